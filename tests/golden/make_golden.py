@@ -1,0 +1,148 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):   python tests/golden/make_golden.py
+The reference's four missing third-party packages are replaced by the stand-ins in tests/golden/_shims
+(see SURVEY.md section 8c / Appendix A); everything else is the reference's own code.  Weights and inputs
+come from oracle/synth.py (hash-keyed on the parameter name) so tests can regenerate them anywhere.
+The .npz files written here are committed; this script documents how they were made.
+"""
+import os
+import sys
+import json
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import transformers  # noqa: F401  (must be imported BEFORE the accelerate stand-in is visible)
+from transformers import T5Config
+
+sys.path.insert(0, os.path.join(HERE, "_shims"))
+sys.path.insert(0, "/root/reference")
+
+from muse_maskgit_pytorch import t5 as ref_t5                      # noqa: E402
+from muse_maskgit_pytorch import VQGanVAE, MaskGitTransformer, MaskGit   # noqa: E402
+from muse_maskgit_pytorch.muse_maskgit_pytorch import cosine_schedule    # noqa: E402
+import math                                                         # noqa: E402
+
+from oracle import synth, shapes                                    # noqa: E402
+
+torch.set_grad_enabled(False)
+
+
+def seed_t5(name, d_model):
+    ref_t5.T5_CONFIGS[name] = dict(config=T5Config(d_model=d_model))
+
+
+def fill(module, table, seed):
+    sd = module.state_dict()
+    got = {k: tuple(v.shape) for k, v in sd.items() if not k.startswith("discr.") and k != "quantizer.mask"}
+    want = {k: tuple(v) for k, v in table.items()}
+    assert got == want, (sorted(set(got) ^ set(want)), [(k, got[k], want[k]) for k in got if k in want and got[k] != want[k]])
+    vals = synth.fill_state_dict(table, seed=seed)
+    for k, v in vals.items():
+        sd[k].copy_(torch.from_numpy(v))
+    return {k: torch.from_numpy(v) for k, v in vals.items()}
+
+
+def text_embeds(name, b, m, d, seed):
+    te = torch.from_numpy(synth.normal(name, (b, m, d), seed))
+    te[1::2, (3 * m) // 4:] = 0.          # padding rows on odd batch entries (exercises context_mask)
+    return te
+
+
+def save(name, **arrs):
+    out = {k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
+# ------------------------------------------------------------------ schedules / top-k counts (known answers)
+def schedule(seq, T):
+    return [max(int((cosine_schedule(t) * seq).item()), 1) for t in torch.linspace(0, 1, T)]
+
+
+known = dict(
+    sched_256_18=schedule(256, 18), sched_1024_18=schedule(1024, 18), sched_16_18=schedule(16, 18),
+    sched_16_6=schedule(16, 6), sched_64_8=schedule(64, 8),
+    topk={str(v): math.ceil((1 - 0.9) * v) for v in (512, 1024, 8192, 65536)},
+)
+assert known["sched_256_18"] == [256, 254, 251, 246, 238, 229, 217, 204, 189, 172, 154, 134, 114, 92, 70, 47, 23, 1]
+with open(os.path.join(HERE, "known_answers.json"), "w") as f:
+    json.dump(known, f, indent=1)
+
+# ------------------------------------------------------------------ G1: config C1 — VAE dim=64 cb=512 on 4x3x32x32
+vae = VQGanVAE(dim=64, codebook_size=512).eval()
+fill(vae, shapes.vae_shapes(64, codebook_size=512), seed=11)
+img = torch.from_numpy(synth.uniform("c1.img", (4, 3, 32, 32), 11))
+fq, ids, _ = vae.encode(img)
+rec = vae.decode_from_ids(ids)
+rec2 = vae(img)
+assert torch.equal(rec, rec2) or (rec - rec2).abs().max() < 1e-6
+fmap = vae.enc_dec.encode(img)
+proj = vae.quantizer.project_in(fmap.permute(0, 2, 3, 1))
+save("vae_c1", ids=ids.long(), recon=rec, fmap=fmap, proj=proj, fmap_q=fq)
+
+# ------------------------------------------------------------------ G2: small VAE (dim=16, layers=2, cb=1024) 2x3x16x16
+vae_s = VQGanVAE(dim=16, layers=2, codebook_size=1024).eval()
+fill(vae_s, shapes.vae_shapes(16, layers=2, codebook_size=1024), seed=12)
+img = torch.from_numpy(synth.uniform("g2.img", (2, 3, 16, 16), 12))
+fq, ids, _ = vae_s.encode(img)
+save("vae_small", ids=ids.long(), recon=vae_s.decode_from_ids(ids), fmap=vae_s.enc_dec.encode(img), fmap_q=fq)
+
+# ------------------------------------------------------------------ G3: small transformer forward (cond / null / CFG)
+for tag, d_text, flash in (("tr_small", 128, False), ("tr_small_proj", 96, False), ("tr_small_flash", 128, True)):
+    seed_t5(f"synth-{d_text}", d_text)
+    tr = MaskGitTransformer(num_tokens=1024, dim=128, seq_len=16, depth=2, dim_head=64, heads=2,
+                            t5_name=f"synth-{d_text}", flash=flash).eval()
+    fill(tr, shapes.transformer_shapes(1024, 128, 16, 2, heads=2, text_dim=d_text), seed=13)
+    ids = torch.from_numpy((synth.uniform("g3.ids", (3, 16), 13) * 1025).astype(np.int64))
+    ids[:, ::3] = 1024
+    te = text_embeds("g3.te", 3, 8, d_text, 13)
+    lc, emb = tr(ids, text_embeds=te, return_embed=True)
+    ln_ = tr(ids, text_embeds=te, cond_drop_prob=1.)
+    cfg = tr.forward_with_cond_scale(ids, text_embeds=te, cond_scale=3.)
+    if tag == "tr_small":
+        save(tag, ids=ids, logits_cond=lc, logits_null=ln_, logits_cfg=cfg, embed=emb)
+    else:
+        save(tag, ids=ids, logits_cfg=cfg, embed=emb)
+
+# ------------------------------------------------------------------ G4: base generate, small (fmap 4x4, V=1024)
+seed_t5("synth-128", 128)
+tr = MaskGitTransformer(num_tokens=1024, dim=128, seq_len=16, depth=2, dim_head=64, heads=2,
+                        t5_name="synth-128", flash=False).eval()
+fill(tr, shapes.transformer_shapes(1024, 128, 16, 2, heads=2, text_dim=128), seed=13)
+vae_s = VQGanVAE(dim=16, layers=2, codebook_size=1024).eval()
+fill(vae_s, shapes.vae_shapes(16, layers=2, codebook_size=1024), seed=12)
+mg = MaskGit(image_size=16, transformer=tr, vae=vae_s).eval()
+te = text_embeds("g4.te", 3, 8, 128, 14)
+tr.encode_text = lambda texts: te
+for T in (6, 18):
+    torch.manual_seed(777)
+    u_probe = torch.zeros(7).uniform_(0, 1)
+    torch.manual_seed(777)
+    grabbed = {}
+    orig = mg.vae.decode_from_ids
+    mg.vae.decode_from_ids = lambda ids_, _o=orig, _g=grabbed: (_g.__setitem__("ids", ids_.clone()), _o(ids_))[1]
+    images = mg.generate(texts=["a"] * 3, timesteps=T, cond_scale=3., temperature=1.)
+    mg.vae.decode_from_ids = orig
+    save(f"gen_small_T{T}", images=images, ids=grabbed["ids"], u_probe=u_probe)
+
+# ------------------------------------------------------------------ G5: super-res generate, small (cond 16x16 -> 32x32; fmap 8x8, 16 cond tokens)
+tr2 = MaskGitTransformer(num_tokens=1024, dim=128, seq_len=64, depth=2, dim_head=64, heads=2,
+                         t5_name="synth-128", flash=False).eval()
+fill(tr2, shapes.transformer_shapes(1024, 128, 64, 2, heads=2, text_dim=128), seed=15)
+mg2 = MaskGit(image_size=32, transformer=tr2, vae=vae_s, cond_image_size=16).eval()
+tr2.encode_text = lambda texts: te[:2]
+cond = torch.from_numpy(synth.uniform("g5.cond", (2, 3, 16, 16), 15))
+torch.manual_seed(778)
+grabbed = {}
+orig = mg2.vae.decode_from_ids
+mg2.vae.decode_from_ids = lambda ids_, _o=orig, _g=grabbed: (_g.__setitem__("ids", ids_.clone()), _o(ids_))[1]
+images = mg2.generate(texts=["a"] * 2, cond_images=cond, timesteps=8)
+mg2.vae.decode_from_ids = orig
+_, cond_ids, _ = mg2.cond_vae.encode(cond)
+save("gen_superres_small", images=images, ids=grabbed["ids"], cond_ids=cond_ids.long())
+print("done")

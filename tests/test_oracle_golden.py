@@ -1,0 +1,99 @@
+"""CPU: the oracle (oracle/muse_oracle.py) against the golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  This is what pins the oracle (task section 3)."""
+import json
+import os
+import numpy as np
+import pytest
+import torch
+
+from oracle import muse_oracle as O
+from oracle import synth
+from tests import util
+
+torch.set_grad_enabled(False)
+CFG = dict(heads=2, depth=2)
+
+
+def test_known_answers():
+    ka = json.load(open(os.path.join(util.GOLDEN, "known_answers.json")))
+    assert O.mask_schedule(256, 18) == ka["sched_256_18"] == [256, 254, 251, 246, 238, 229, 217, 204, 189, 172, 154, 134, 114, 92, 70, 47, 23, 1]
+    assert O.mask_schedule(1024, 18) == ka["sched_1024_18"]
+    assert O.mask_schedule(16, 6) == ka["sched_16_6"] and O.mask_schedule(64, 8) == ka["sched_64_8"]
+    for v, k in ka["topk"].items():
+        assert O.top_k_count(int(v), 0.9) == k
+    assert O.top_k_count(65536, 0.9) == 6554
+
+
+def test_vae_c1_config():
+    g = util.golden("vae_c1")
+    sd = util.vae_sd(64, 4, 512, seed=11)
+    img = torch.from_numpy(synth.uniform("c1.img", (4, 3, 32, 32), 11))
+    fmap = O.vae_encode_fmap(sd, img)
+    assert torch.allclose(fmap, g["fmap"], atol=1e-5, rtol=1e-5)
+    q, ids = O.vae_encode(sd, img)
+    assert torch.equal(ids, g["ids"]) and ids.min() >= 0 and ids.max() < 512
+    assert torch.allclose(q, g["fmap_q"], atol=1e-5)
+    rec = O.vae_decode_from_ids(sd, ids, 9)
+    assert torch.allclose(rec, g["recon"], atol=1e-5, rtol=1e-5)
+
+
+def test_vae_small():
+    g = util.golden("vae_small")
+    sd = util.vae_sd(16, 2, 1024, seed=12)
+    img = torch.from_numpy(synth.uniform("g2.img", (2, 3, 16, 16), 12))
+    q, ids = O.vae_encode(sd, img)
+    assert torch.equal(ids, g["ids"])
+    assert torch.allclose(O.vae_decode_from_ids(sd, ids, 10), g["recon"], atol=1e-5)
+
+
+def test_lfq_is_l2_argmin_over_sign_codebook():
+    """Pin for the un-vendored LFQ: ids == argmin_k ||x - c_k||^2 over the explicit {+-1}^d codebook
+    (MSB-first bit order), including exact-zero coordinates (-> bit 0 -> lower index)."""
+    d = 6
+    x = torch.from_numpy(synth.dyadic("lfq.x", (200, d), bits=3, span=2.0))
+    x[::7, 2] = 0.
+    codes = torch.tensor([[1. if (k >> (d - 1 - i)) & 1 else -1. for i in range(d)] for k in range(2 ** d)])
+    _, ids = O.lfq_quantize({}, x.t().reshape(1, d, 200, 1).permute(0, 1, 2, 3))
+    brute = O.vq_l2_argmin(x, codes)
+    assert torch.equal(ids.reshape(-1), brute)
+
+
+@pytest.mark.parametrize("tag,d_text", [("tr_small", 128), ("tr_small_proj", 96), ("tr_small_flash", 128)])
+def test_transformer_forward(tag, d_text):
+    g = util.golden(tag)
+    sd = util.transformer_sd(1024, 128, 16, 2, 2, seed=13, text_dim=d_text)
+    te = util.text_embeds("g3.te", 3, 8, d_text, 13)
+    ids = g["ids"]
+    cfg_logits, embed = O.forward_with_cond_scale(sd, CFG, ids, te, cond_scale=3.)
+    tol = 2e-5 if tag != "tr_small_flash" else 1e-4     # flash stand-in: tiled online softmax, same math
+    assert torch.allclose(embed, g["embed"], atol=tol, rtol=1e-4)
+    assert torch.allclose(cfg_logits, g["logits_cfg"], atol=5 * tol, rtol=1e-4)
+    if "logits_null" in g:
+        assert torch.allclose(O.transformer_forward(sd, CFG, ids, te, drop_text=True), g["logits_null"], atol=tol, rtol=1e-4)
+
+
+@pytest.mark.parametrize("T", [6, 18])
+def test_generate_small(T):
+    g = util.golden(f"gen_small_T{T}")
+    torch.manual_seed(777)
+    if not torch.equal(torch.zeros(7).uniform_(0, 1), g["u_probe"]):
+        pytest.skip("torch CPU generator differs from the one that made the fixture")
+    sd = util.transformer_sd(1024, 128, 16, 2, 2, seed=13, text_dim=128)
+    vsd = util.vae_sd(16, 2, 1024, seed=12)
+    te = util.text_embeds("g4.te", 3, 8, 128, 14)
+    images, ids = O.generate(sd, CFG, vsd, 10, te, 4, util.torch_noise_fn(777), timesteps=T)
+    assert torch.equal(ids.view(3, 4, 4), g["ids"])
+    assert torch.allclose(images, g["images"], atol=1e-5)
+
+
+def test_generate_superres_small():
+    g = util.golden("gen_superres_small")
+    sd = util.transformer_sd(1024, 128, 64, 2, 2, seed=15, text_dim=128)
+    vsd = util.vae_sd(16, 2, 1024, seed=12)
+    te = util.text_embeds("g4.te", 3, 8, 128, 14)[:2]
+    cond = torch.from_numpy(synth.uniform("g5.cond", (2, 3, 16, 16), 15))
+    _, cond_ids = O.vae_encode(vsd, cond)
+    assert torch.equal(cond_ids, g["cond_ids"])
+    images, ids = O.generate(sd, CFG, vsd, 10, te, 8, util.torch_noise_fn(778), cond_images=cond, timesteps=8)
+    assert torch.equal(ids.view(2, 8, 8), g["ids"])
+    assert torch.allclose(images, g["images"], atol=1e-5)
