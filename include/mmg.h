@@ -1,0 +1,243 @@
+/*
+ * mmg.h — C-ABI of libmmg.so: hand-written sm_100a kernels for the MaskGit.generate() hot path.
+ *
+ * This is the drop-in boundary ("lower face").  Every entry point is
+ *     extern "C" int mmg_<op>(const mmg_<op>_args* a, void* cuda_stream);
+ * with a POD argument block of raw DEVICE pointers + sizes.  Conventions:
+ *   - returns 0 on success, a negative MMG_E* code otherwise; never throws, never allocates device memory,
+ *     never synchronises the host; asynchronous on `cuda_stream` (a cudaStream_t) and CUDA-graph capturable;
+ *   - no ownership transfer; the caller (PyTorch) owns all buffers;
+ *   - mmg_last_error() returns a thread-local, human readable description of the last failure;
+ *   - activations are row-major "token-major" matrices [rows, channels] (images: NHWC); `dtype` selects the
+ *     operand type of a matrix product: MMG_BF16 -> tcgen05 tensor-core path (fp32 accumulate in TMEM),
+ *     MMG_F32 -> fp32 CUDA-core path ("parity precision").  There is no CPU path in this library.
+ *
+ * Each function cites the reference code it replaces (paths relative to /root/reference/muse_maskgit_pytorch/).
+ */
+#ifndef MMG_H_
+#define MMG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMG_VERSION 100
+
+/* error codes */
+#define MMG_OK            0
+#define MMG_EINVAL       -1   /* bad argument / unsupported shape */
+#define MMG_ECUDA        -2   /* CUDA runtime / driver error (see mmg_last_error) */
+#define MMG_EUNSUPPORTED -3   /* device is not sm_100 */
+
+/* operand dtypes */
+#define MMG_F32  0
+#define MMG_BF16 1
+
+int         mmg_version(void);
+const char* mmg_last_error(void);
+/* Number of kernel launches issued through this library by the calling process (bench.py "gpu_launches"). */
+int64_t     mmg_launch_count(void);
+/* sizeof() of the argument block of entry point `name` ("mmg_linear", ...; "mmg_epilogue" for mmg_epilogue_args): lets a
+ * foreign-language binding verify its struct mirror. Returns 0 for unknown names. */
+int         mmg_sizeof(const char* name);
+
+/* ------------------------------------------------------------------------------------------------
+ * Matrix product with fused epilogue:  C[M,N] = A[M,K] * W[N,K]^T  (+ epilogue)
+ * replaces: every nn.Linear on the path (muse_maskgit_pytorch.py:85,88,118,119,124,225,233) and, through
+ * mmg_conv2d / mmg_conv_transpose2d below, every nn.Conv2d / nn.ConvTranspose2d (vqgan_vae.py:224-232,255-277).
+ * ---------------------------------------------------------------------------------------------- */
+enum mmg_epilogue {
+  MMG_EPI_STORE      = 0, /* out[r, c] = acc (+bias[c]) (+leaky_relu 0.1 if act==1); out dtype = out_dtype          */
+  MMG_EPI_RESIDUAL   = 1, /* out[r, c] = acc (+bias[c]) + resid[r, c]; out/resid dtype = out_dtype (may alias)      */
+  MMG_EPI_GEGLU      = 2, /* W rows interleaved in blocks of 32: [x(32) | gate(32)]; out[r, c/2] = gate*gelu_erf(x) */
+  MMG_EPI_GLU        = 3, /* same interleave, with bias: out = (a+ba) * sigmoid(g+bg)         (nn.GLU, vqgan_vae.py:256) */
+  MMG_EPI_QKV        = 4, /* N = (nq+nk+nv)*64 head-columns: l2norm(q)*q_scale, l2norm(k)*k_scale, v -> per-head layouts */
+  MMG_EPI_CONVT      = 5, /* conv-transpose parity scatter: out pixel (2y+py, 2x+px) = leaky(acc + bias)             */
+  MMG_EPI_CONVT_RGB  = 6, /* CONVT followed by the fused final 1x1 conv (C -> channels<=4), fp32 NCHW output          */
+};
+
+typedef struct {
+  void*        out;        /* see enum; [M, ldo]                                                                 */
+  int64_t      ldo;        /* leading dimension of out (elements)                                                */
+  int32_t      out_dtype;  /* MMG_F32 / MMG_BF16                                                                 */
+  int32_t      act;        /* 0 none, 1 leaky_relu(0.1)                                                          */
+  const float* bias;       /* [N] or NULL (for GEGLU/GLU: interleaved like W rows)                               */
+  const void*  resid;      /* RESIDUAL: [M, ldr] of out_dtype                                                    */
+  int64_t      ldr;
+  /* QKV: q -> q_out[(b*heads+h), t, 64]; k,v -> k_out/v_out[(b*heads+h), key_off + t, 64] with row r = b*tokens + t */
+  void*        q_out; void* k_out; void* v_out;   /* dtype = out_dtype                                            */
+  const float* q_scale; const float* k_scale;     /* [64]                                                         */
+  const void*  null_k; const void* null_v;        /* optional [heads, 64] of out_dtype: written to key row 0 of every
+                                                     (b, h) by the thread that owns token 0 (learned null key/value) */
+  int32_t      heads, tokens, q_rows, kv_rows, key_off, nq_heads, nk_heads, nv_heads;
+  /* CONVT(_RGB): input geometry of the GEMM rows (b, y, x) and the output parity                                  */
+  int32_t      H, W, py, px;
+  const float* rgb_w;      /* CONVT_RGB: [channels, N] fp32 1x1 weights, rgb_b [channels]                          */
+  const float* rgb_b;
+  int32_t      rgb_channels;
+  int32_t      _pad;
+} mmg_epilogue_args;
+
+typedef struct {
+  const void* a;           /* [M, lda] operand dtype                                                             */
+  const void* w;           /* [N, ldw] operand dtype (nn.Linear weight layout, K contiguous)                     */
+  int64_t M, N, K, lda, ldw;
+  int32_t dtype;           /* MMG_BF16: tcgen05 path (K % 64 == 0, N % 64 == 0, 16B-aligned rows); MMG_F32: CUDA cores */
+  int32_t epilogue;        /* enum mmg_epilogue                                                                   */
+  mmg_epilogue_args epi;
+} mmg_linear_args;
+int mmg_linear(const mmg_linear_args* a, void* stream);
+
+/* Convolutions as implicit GEMM over NHWC activations; weights pre-packed [Cout, taps*Cin] (tap-major, Cin
+ * contiguous).  kind: 0 = 1x1; 1 = 3x3 stride 1 pad 1; 2 = 4x4 stride 2 pad 1; 3 = 5x5 stride 1 pad 2.
+ * replaces: nn.Conv2d at vqgan_vae.py:224,231,232,255,258,261,271,274,277.                                        */
+typedef struct {
+  const void* x;           /* [B, H, W, Cin]                                                                     */
+  const void* w;           /* [Cout, taps*Cin]                                                                   */
+  int32_t B, H, W, Cin, Cout, kind;
+  int32_t dtype, epilogue; /* STORE / RESIDUAL / GLU                                                             */
+  mmg_epilogue_args epi;   /* rows of `out` are output pixels (b, y, x) in NHWC order                            */
+} mmg_conv2d_args;
+int mmg_conv2d(const mmg_conv2d_args* a, void* stream);
+
+/* ConvTranspose2d(k=4, s=2, p=1) as 4 parity-class GEMMs (K = 4*Cin each).  w: [4 parities][Cout, 4*Cin].
+ * replaces: nn.ConvTranspose2d + LeakyReLU at vqgan_vae.py:225 (and, with CONVT_RGB, the 1x1 at vqgan_vae.py:232). */
+typedef struct {
+  const void* x;           /* [B, H, W, Cin]                                                                     */
+  const void* w;           /* [4, Cout, 4*Cin]                                                                   */
+  int32_t B, H, W, Cin, Cout;
+  int32_t dtype, epilogue; /* CONVT or CONVT_RGB                                                                 */
+  mmg_epilogue_args epi;   /* out: [B, 2H, 2W, Cout] (CONVT) or fp32 [B, channels, 2H, 2W] (CONVT_RGB)           */
+} mmg_conv_transpose2d_args;
+int mmg_conv_transpose2d(const mmg_conv_transpose2d_args* a, void* stream);
+
+/* First encoder conv: 5x5, Cin = channels (3), fp32 NCHW image in, NHWC act out.  replaces vqgan_vae.py:231.     */
+typedef struct {
+  const float* img;        /* [B, C, H, W] fp32                                                                  */
+  const float* w;          /* [Cout, C, 5, 5] fp32 (reference layout)                                            */
+  const float* bias;       /* [Cout]                                                                             */
+  void*        out;        /* [B, H, W, Cout] out_dtype                                                          */
+  int32_t B, C, H, W, Cout, out_dtype;
+} mmg_conv_in_args;
+int mmg_conv_in(const mmg_conv_in_args* a, void* stream);
+
+/* GroupNorm(groups, eps 1e-5) over NHWC, in place, optional LeakyReLU(0.1).  replaces vqgan_vae.py:257,260,272-276. */
+typedef struct {
+  void*        x;          /* [B, HW, C] dtype, normalised in place                                              */
+  const float* gamma; const float* beta;
+  int32_t B, HW, C, groups, dtype, act;
+} mmg_groupnorm_args;
+int mmg_groupnorm(const mmg_groupnorm_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm (eps 1e-5, gamma only — beta is a zero buffer): muse_maskgit_pytorch.py:63-70.
+ *   y[r, :] = LN(x[r, :width] (+ add[:]) ) * gamma, columns >= width are written as 0 up to ldy.
+ *   If x_out != NULL the (x + add) sum is also written back (fp32) — used for the constant null-CFG cross-attn term.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void*  x;  int32_t x_dtype;  int32_t y_dtype;
+  void*        y;
+  const float* gamma;      /* [width]                                                                            */
+  const float* add;        /* [width] or NULL                                                                    */
+  float*       x_out;      /* fp32 [rows, ldx] or NULL                                                           */
+  int64_t rows, width, ldx, ldy;
+} mmg_layernorm_args;
+int mmg_layernorm(const mmg_layernorm_args* a, void* stream);
+
+/* x[r, :] = token_emb[ids[r]] + pos_emb[r % n]  (fp32): muse_maskgit_pytorch.py:322-323; `copies` replicas of the
+ * whole [rows, dim] block are written back to back (cond / null CFG branches share the embedding).               */
+typedef struct {
+  const int64_t* ids; const float* token_emb; const float* pos_emb;
+  float* x; int64_t rows, n, dim; int32_t copies; int32_t use_pos;
+} mmg_embed_args;
+int mmg_embed(const mmg_embed_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention core: out[b, t, h*64:(h+1)*64] = softmax(scale * q.k^T + key_mask) v   with dh = 64.
+ * q [BH, Tq, 64], k/v [BH, Tk_alloc, 64] already l2-normalised/scaled (epilogue MMG_EPI_QKV); key 0 is the null key.
+ * replaces: Attend.forward / flash_attn (attend.py:66-140) + the head split/merge in Attention.forward
+ * (muse_maskgit_pytorch.py:143-161).  key_mask: [B, Tk] uint8 (1 = attend) or NULL; masked logits = -FLT_MAX.     */
+typedef struct {
+  const void* q; const void* k; const void* v; void* out;
+  const uint8_t* key_mask;
+  int32_t B, heads, Tq, Tk, Tk_alloc, dtype;
+  int64_t ldo;             /* out row stride (elements) = heads*64 normally                                      */
+  int32_t kv_batch_stride_zero;  /* 1: k/v are shared by all batch entries (per head only)                        */
+  float   scale;
+} mmg_attention_args;
+int mmg_attention(const mmg_attention_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampler.  replaces muse_maskgit_pytorch.py:556-609 (the per-step tail of MaskGit.generate).
+ * ---------------------------------------------------------------------------------------------- */
+/* re-mask: select the num_masked highest scores per batch row (ties: lowest position first), write mask_id there,
+ * set all scores to -1e5, and emit the ascending list of masked positions (muse_maskgit_pytorch.py:561-563).     */
+typedef struct {
+  int64_t* ids; float* scores; int32_t* masked_pos;   /* [B, n], [B, n], [B, num_masked]                          */
+  int32_t B, n, num_masked; int64_t mask_id;
+} mmg_remask_args;
+int mmg_remask(const mmg_remask_args* a, void* stream);
+
+/* Final LayerNorm + classifier-free-guidance combine on the masked rows only, in embedding space:
+ *   e[j] = LN(x_null[r]) + (LN(x_cond[r]) - LN(x_null[r])) * cond_scale,  r = b*n + masked_pos[b, j]
+ * (to_logits is linear and bias-free, so W e == null + (cond - null) * scale of muse_maskgit_pytorch.py:254).    */
+typedef struct {
+  const float* x_cond; const float* x_null;  /* [B*n, dim] fp32; x_null may be NULL (cond_scale == 1)             */
+  const float* gamma; const int32_t* masked_pos;
+  void* e; int32_t e_dtype;
+  int32_t B, n, num_masked, dim; float cond_scale;
+} mmg_final_embed_args;
+int mmg_final_embed(const mmg_final_embed_args* a, void* stream);
+
+/* top-k filter + gumbel-argmax + confidence score for R logits rows (muse_maskgit_pytorch.py:576-609, 403-418):
+ *   keep the k largest logits of each row (ties at the threshold: lowest index first);
+ *   pred = argmax_v( logit_v / max(T, 1e-10) - log(-log(u_v)) ),   u clamped at 1e-20 as the reference's log();
+ *   score = 1 - softmax(logits)[pred];  ids[b, pos] = pred;  scores[b, pos] = score.
+ * Noise: `u` != NULL -> injected uniforms, u[(b*n + pos) * V + v] (parity mode: the tensor the reference would
+ * draw); else Philox4x32-10(seed, counter = (global row, v)) so results do not depend on the GPU count.          */
+typedef struct {
+  const float* logits;     /* [R, V] fp32, R = B*num_masked, row j of batch b at b*num_masked + j                  */
+  const int32_t* masked_pos;
+  int64_t* ids; float* scores;             /* [B, n]                                                              */
+  const float* u;          /* [B, n, V] or NULL                                                                   */
+  int32_t B, n, num_masked, V, k;
+  float temperature;
+  uint64_t seed; uint64_t step; int64_t row_offset;  /* global row = row_offset + b*n + pos                        */
+} mmg_logits_sample_args;
+int mmg_logits_sample(const mmg_logits_sample_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VQ lookup.  replaces the quantizer calls at vqgan_vae.py:424 and 429-435.
+ * ---------------------------------------------------------------------------------------------- */
+/* LFQ: ids[t] = sum_i (x[t,:].w_in[i,:] + b_in[i] > 0) << (bits-1-i)  — the nearest-codebook L2 argmin over {+-1}^bits. */
+typedef struct {
+  const void* x; int32_t dtype;            /* [T, D] token-major fmap                                              */
+  const float* w_in; const float* b_in;    /* [bits, D], [bits]; NULL -> identity (D == bits)                     */
+  int64_t* ids; int64_t T; int32_t D, bits;
+} mmg_vq_lfq_encode_args;
+int mmg_vq_lfq_encode(const mmg_vq_lfq_encode_args* a, void* stream);
+
+/* explicit codebook: ids[t] = argmin_k ||x_t - e_k||^2 (first index on ties); coalesced codebook scan + warp argmin */
+typedef struct {
+  const float* x; const float* codebook;   /* [T, D], [K, D] fp32                                                  */
+  int64_t* ids; int64_t T; int32_t K, D;
+} mmg_vq_l2_argmin_args;
+int mmg_vq_l2_argmin(const mmg_vq_l2_argmin_args* a, void* stream);
+
+/* ids -> codes -> project_out: out[t, :] = sum_i (+-1)_i * w_out[:, i] + b_out  (LFQ.indices_to_codes)            */
+typedef struct {
+  const int64_t* ids; const float* w_out; const float* b_out;   /* w_out [D, bits]                                 */
+  void* out; int32_t dtype; int64_t T; int32_t D, bits;
+} mmg_vq_decode_codes_args;
+int mmg_vq_decode_codes(const mmg_vq_decode_codes_args* a, void* stream);
+
+/* dtype conversion / layout helpers used by the host mirror */
+typedef struct { const void* src; void* dst; int64_t n; int32_t src_dtype, dst_dtype; } mmg_cast_args;
+int mmg_cast(const mmg_cast_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMG_H_ */

@@ -1,0 +1,212 @@
+// tcgen05 attention for dh = 64 (bf16 operands, fp32 softmax statistics).
+//
+// One CTA = one (batch, head, 128-query tile).  Keys are walked in nb blocks of KB (<= 256, multiple of 32) keys, twice:
+//   pass A:  S = Q K^T (tcgen05.mma, M=128, N=KB, 4 k-steps) -> TMEM -> per-row running max        (no P, no V traffic)
+//   pass B:  S again -> p = exp2((s - max) * scale*log2e) in registers (masked / out-of-range keys -> 0), row sums in fp32,
+//            P (bf16) written to shared memory in the K-major SWIZZLE_128B operand layout, O += P V (tcgen05.mma, M=128,
+//            N=64, KB/16 k-steps, V consumed MN-major straight from its TMA tile) accumulating in TMEM across blocks.
+//   finally: O / rowsum -> bf16 -> out[b, t, h*64 : (h+1)*64].
+// The exact two-pass softmax (true row max, as attend.py:131) avoids the rescaling chain of an online softmax; the second
+// Q K^T costs 4 extra MMAs per block.  Warp 4 is the control warp (one elected lane: TMA loads + MMA issue); warps 0-3
+// own TMEM lane quarters 0-3 = query rows.
+#pragma once
+#include "mmg_common.cuh"
+#include "mmg_sm100.cuh"
+#include <cudaTypedefs.h>
+#include <float.h>
+
+namespace mmg {
+
+struct alignas(64) AttnTcParams {
+  CUtensorMap tma_q, tma_k, tma_v;
+  const uint8_t* key_mask;
+  bf16* out;
+  int heads, Tq, Tk, Tk_alloc, nb, KB, kv_shared;
+  int64_t ldo;
+  float scale_log2e;
+};
+
+template <uint32_t TMEM_COLS>
+__global__ void __launch_bounds__(160, 1)
+attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  using namespace sm100;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int KB = p.KB;
+  const int kv_bytes = KB * 128;
+  uint8_t* sQ = smem;                         // 128 x 64 bf16
+  uint8_t* sK = sQ + 16384;                   // KB x 64
+  uint8_t* sV = sK + ((kv_bytes + 1023) & ~1023);
+  uint8_t* sP = sV + ((kv_bytes + 1023) & ~1023);      // ceil(KB/64) sub-tiles of 128 x 64 bf16
+  const int p_tiles = (KB + 63) / 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + p_tiles * 16384);
+  uint64_t* bar_q = bars + 0; uint64_t* bar_kv = bars + 1; uint64_t* bar_s = bars + 2;
+  uint64_t* bar_sdone = bars + 3; uint64_t* bar_p = bars + 4; uint64_t* bar_pv = bars + 5;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / p.heads, h = bh % p.heads;
+  const int q0 = blockIdx.x * 128;
+  const int kvh = p.kv_shared ? h : bh;
+
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&p.tma_q); prefetch_tmap(&p.tma_k); prefetch_tmap(&p.tma_v);
+    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_sdone, 4); mbar_init(bar_p, 4); mbar_init(bar_pv, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tS = tmem_base;                       // KB fp32 columns
+  const uint32_t tO = tmem_base + TMEM_COLS - 64;      // 64 fp32 columns
+
+  if (warp == 4) {
+    if (elect_one()) {
+      const uint32_t idesc_s = idesc_bf16_f32(128, (uint32_t)KB, false, false);
+      const uint32_t idesc_o = idesc_bf16_f32(128, 64, false, true);          // B (= V) is MN-major
+      mbar_expect_tx(bar_q, 16384);
+      tma_load_2d(sQ, &p.tma_q, bar_q, 0, bh * p.Tq + q0);
+      mbar_wait(bar_q, 0);
+      uint32_t ph_kv = 0, ph_sdone = 0, ph_p = 0, ph_pv = 0;
+      const uint64_t qdesc = smem_desc_kmajor_sw128(smem_u32(sQ));
+      const uint64_t kdesc = smem_desc_kmajor_sw128(smem_u32(sK));
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int blk = 0; blk < p.nb; ++blk) {
+          const int krow = kvh * p.Tk_alloc + blk * KB;
+          mbar_expect_tx(bar_kv, pass == 0 ? kv_bytes : 2 * kv_bytes);
+          tma_load_2d(sK, &p.tma_k, bar_kv, 0, krow);
+          if (pass == 1) tma_load_2d(sV, &p.tma_v, bar_kv, 0, krow);
+          mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
+          umma_commit(bar_s);
+          if (pass == 0) {
+            mbar_wait(bar_sdone, ph_sdone); ph_sdone ^= 1;      // softmax warps consumed S; K smem is free (MMA retired before S was readable)
+          } else {
+            mbar_wait(bar_p, ph_p); ph_p ^= 1;                  // P staged in smem (and S consumed)
+            tc_fence_after();
+            const int ksteps = KB / 16;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t pa = smem_u32(sP) + (ks >> 2) * 16384 + (ks & 3) * 32;
+              const uint64_t pdesc = smem_desc_kmajor_sw128(pa);
+              const uint64_t vdesc = smem_desc_mnmajor_sw128(smem_u32(sV) + ks * 2048, 1024);
+              umma_f16(tO, pdesc, vdesc, idesc_o, (blk | ks) ? 1u : 0u);
+            }
+            umma_commit(bar_pv);
+            mbar_wait(bar_pv, ph_pv); ph_pv ^= 1;               // K/V/P smem free again; on the last block: O complete
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax warps: thread = query row =====================
+    const int r = warp * 32 + lane;
+    const int qi = q0 + r;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const uint8_t* km = p.key_mask ? p.key_mask + (int64_t)b * (p.Tk - 1) : nullptr;
+    uint32_t ph_s = 0, ph_pv = 0;
+    float row_max = -FLT_MAX, row_sum = 0.f;
+    float mneg = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1) mneg = row_max * p.scale_log2e;
+      for (int blk = 0; blk < p.nb; ++blk) {
+        mbar_wait(bar_s, ph_s); ph_s ^= 1;
+        tc_fence_after();
+        for (int c = 0; c < KB; c += 32) {
+          float s[32];
+          tmem_ld_32x32b_x32(tS + lane_base + c, s);
+          tmem_ld_wait();
+          const int j0 = blk * KB + c;
+          if (pass == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int j = j0 + i;
+              // masked keys take the value -FLT_MAX in the reference; they only matter for the max if every key is masked,
+              // which cannot happen (key 0, the null key, is never masked)
+              const bool live = j < p.Tk && (j == 0 || !km || km[j - 1]);
+              if (live) row_max = fmaxf(row_max, s[i]);
+            }
+          } else {
+            uint32_t packed[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float pv[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int j = j0 + i + e;
+                const bool live = j < p.Tk && (j == 0 || !km || km[j - 1]);
+                pv[e] = live ? exp2f(fmaf(s[i + e], p.scale_log2e, -mneg)) : 0.f;
+                row_sum += pv[e];
+              }
+              __nv_bfloat162 t = __floats2bfloat162_rn(pv[0], pv[1]);
+              packed[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            // P[r, c .. c+31] -> sub-tile (c / 64), 16-byte chunks (c % 64) / 8 .. +3, 128B swizzle: chunk ^= (r & 7)
+            uint8_t* tile = sP + (c >> 6) * 16384 + r * 128;
+            const int ch0 = (c & 63) >> 3;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int ch = (ch0 + q4) ^ (r & 7);
+              *reinterpret_cast<uint4*>(tile + ch * 16) = make_uint4(packed[q4 * 4], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
+            }
+          }
+        }
+        tc_fence_before();
+        if (pass == 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_sdone);
+        } else {
+          fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_p);
+          mbar_wait(bar_pv, ph_pv); ph_pv ^= 1;  // this block's P.V retired (P smem reusable; after the last block O is final)
+        }
+      }
+    }
+    tc_fence_after();
+    const float inv = 1.f / row_sum;
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {
+      float o[32];
+      tmem_ld_32x32b_x32(tO + lane_base + c, o);
+      tmem_ld_wait();
+      if (qi < p.Tq) {
+        bf16* dst = p.out + ((int64_t)b * p.Tq + qi) * p.ldo + h * 64 + c;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 t;
+          __nv_bfloat162 a0 = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv), a1 = __floats2bfloat162_rn(o[i + 2] * inv, o[i + 3] * inv);
+          __nv_bfloat162 a2 = __floats2bfloat162_rn(o[i + 4] * inv, o[i + 5] * inv), a3 = __floats2bfloat162_rn(o[i + 6] * inv, o[i + 7] * inv);
+          t.x = *reinterpret_cast<uint32_t*>(&a0); t.y = *reinterpret_cast<uint32_t*>(&a1);
+          t.z = *reinterpret_cast<uint32_t*>(&a2); t.w = *reinterpret_cast<uint32_t*>(&a3);
+          *reinterpret_cast<uint4*>(dst + i) = t;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<TMEM_COLS>(tmem_base); }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+inline bool attention_tc_supported(const mmg_attention_args* a) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return al(a->q) && al(a->k) && al(a->v) && al(a->out) && (a->ldo % 8 == 0) && a->Tk <= 4096;
+}
+
+inline void attn_blocks(int Tk, int* nb, int* KB) {
+  *nb = (Tk + 255) / 256;
+  int kb = (Tk + *nb - 1) / *nb;
+  kb = (kb + 31) / 32 * 32;
+  if (kb < 32) kb = 32;
+  *KB = kb;
+}
+
+int attention_tc_launch(const mmg_attention_args* a, cudaStream_t st);
+
+}  // namespace mmg

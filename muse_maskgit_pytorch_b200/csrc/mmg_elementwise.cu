@@ -1,0 +1,297 @@
+// HBM-bound row kernels: LayerNorm, token embedding, final-LN + CFG combine, GroupNorm, first 5x5 conv, casts.
+#include "mmg_common.cuh"
+
+namespace mmg {
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row is held in registers (width <= 32*4*MAXV), two-pass mean/variance in fp32
+// exactly as F.layer_norm (biased variance, eps 1e-5).  ref: muse_maskgit_pytorch.py:63-70
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 16;   // float4 chunks per lane -> width <= 2048
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ add,
+                 float* __restrict__ x_out, int64_t rows, int width, int64_t ldx, int64_t ldy) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TX* xr = x + row * ldx;
+  float v[LN_MAXV * 4];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = 0.f;
+      if (c + j < width) { t = to_f(xr[c + j]); if (add) t += __ldg(add + c + j); }
+      v[i * 4 + j] = t; sum += t;
+    }
+  }
+  sum = warp_sum(sum);
+  const float mean = sum / (float)width;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (c + j < width) { const float d = v[i * 4 + j] - mean; sq += d * d; }
+  }
+  sq = warp_sum(sq);
+  const float rstd = rsqrtf(sq / (float)width + 1e-5f);
+  TY* yr = y + row * ldy;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (c + j < width) {
+        yr[c + j] = from_f<TY>((v[i * 4 + j] - mean) * rstd * __ldg(gamma + c + j));
+        if (x_out) x_out[row * ldx + c + j] = v[i * 4 + j];
+      } else if (c + j < ldy) {
+        yr[c + j] = from_f<TY>(0.f);
+      }
+    }
+  }
+}
+
+// x[copy][r, :] = token_emb[ids[r]] + pos_emb[r % n]        ref: muse_maskgit_pytorch.py:322-323 (and 316 with use_pos = 0)
+__global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                             float* __restrict__ x, int64_t rows, int64_t n, int64_t dim, int copies, int use_pos) {
+  const int64_t row = blockIdx.x;
+  const int64_t id = ids[row];
+  const float4* t = reinterpret_cast<const float4*>(tok + id * dim);
+  const float4* p = reinterpret_cast<const float4*>(pos + (row % n) * dim);
+  for (int c = threadIdx.x; c < dim / 4; c += blockDim.x) {
+    float4 a = __ldg(t + c);
+    if (use_pos) { const float4 b = __ldg(p + c); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+    for (int k = 0; k < copies; ++k) reinterpret_cast<float4*>(x + ((int64_t)k * rows + row) * dim)[c] = a;
+  }
+}
+
+// e[j] = LNn + (LNc - LNn) * s on the masked rows; one warp per masked row; dim <= 2048.
+template <typename TE>
+__global__ void __launch_bounds__(256)
+final_embed_kernel(const float* __restrict__ xc, const float* __restrict__ xn, const float* __restrict__ gamma,
+                   const int32_t* __restrict__ masked_pos, TE* __restrict__ e, int B, int n, int num_masked, int dim, float s) {
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= (int64_t)B * num_masked) return;
+  const int b = (int)(j / num_masked);
+  const int64_t row = (int64_t)b * n + masked_pos[j];
+  float out[LN_MAXV * 4];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV * 4; ++i) out[i] = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {
+    const float* xr = (pass == 0 ? xc : xn);
+    if (!xr) continue;
+    xr += row * dim;
+    float v[LN_MAXV * 4]; float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float t = (c + k < dim) ? xr[c + k] : 0.f; v[i * 4 + k] = t; sum += t; }
+    }
+    const float mean = warp_sum(sum) / (float)dim;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (c + k < dim) { const float d = v[i * 4 + k] - mean; sq += d * d; }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)dim + 1e-5f);
+    // cond pass contributes s * LNc, null pass (1 - s) * LNn:  LNn + (LNc - LNn) * s
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (c + k < dim) {
+        const float ln = (v[i * 4 + k] - mean) * rstd * __ldg(gamma + c + k);
+        // keep the reference's association: null + (cond - null) * scale
+        if (pass == 0) out[i * 4 + k] = ln; else out[i * 4 + k] = ln + (out[i * 4 + k] - ln) * s;
+      }
+    }
+  }
+  TE* er = e + j * dim;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (c + k < dim) er[c + k] = from_f<TE>(out[i * 4 + k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm over NHWC [B, HW, C]: one CTA per (b, group); mean, then centred variance, then apply (3 passes over an
+// L2-resident slab).  eps 1e-5, affine, optional LeakyReLU(0.1).   ref: vqgan_vae.py:257,260,272-276
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? red[l] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+groupnorm_kernel(T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int groups, int act) {
+  __shared__ float red[32];
+  const int b = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int cg = C / groups;
+  T* base = x + (int64_t)b * HW * C + g * cg;
+  const int total = HW * cg;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) s += to_f(base[(int64_t)(i / cg) * C + (i % cg)]);
+  const float mean = block_sum(s, red) / (float)total;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) { const float d = to_f(base[(int64_t)(i / cg) * C + (i % cg)]) - mean; q += d * d; }
+  const float rstd = rsqrtf(block_sum(q, red) / (float)total + 1e-5f);
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int c = i % cg; T* p = base + (int64_t)(i / cg) * C + c;
+    float v = (to_f(*p) - mean) * rstd * __ldg(gamma + g * cg + c) + __ldg(beta + g * cg + c);
+    if (act) v = leaky01(v);
+    *p = from_f<T>(v);
+  }
+}
+
+// First encoder conv: 5x5 pad 2, Cin = C (<= 4), fp32 NCHW image -> NHWC activations.  K = 25*C is tiny; persistent
+// CTAs keep the transposed weights [K][Cout] in shared memory and sweep groups of 8 pixels (patches staged in smem,
+// broadcast reads), thread = output channel, stores coalesced along Cout.   ref: vqgan_vae.py:231
+constexpr int CI_PIX = 8;
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_in_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
+               int B, int C, int H, int W, int Cout) {
+  extern __shared__ float ws[];                   // [K][Cout] then patches [CI_PIX][K]
+  const int K = C * 25;
+  float* patch = ws + (size_t)K * Cout;
+  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) { const int co = i / K, k = i - co * K; ws[k * Cout + co] = w[i]; }
+  const int64_t pixels = (int64_t)B * H * W;
+  for (int64_t p0 = (int64_t)blockIdx.x * CI_PIX; p0 < pixels; p0 += (int64_t)gridDim.x * CI_PIX) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < CI_PIX * K; i += blockDim.x) {
+      const int pi = i / K, k = i - pi * K; const int64_t pix = p0 + pi;
+      float v = 0.f;
+      if (pix < pixels) {
+        const int b = (int)(pix / ((int64_t)H * W)); const int rem = (int)(pix - (int64_t)b * H * W); const int y = rem / W, xx = rem - y * W;
+        const int c = k / 25, r = (k % 25) / 5, sx = k % 5; const int iy = y + r - 2, ix = xx + sx - 2;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((int64_t)b * C + c) * H + iy) * W + ix);
+      }
+      patch[i] = v;
+    }
+    __syncthreads();
+    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+      float acc[CI_PIX];
+      const float bv = bias ? bias[co] : 0.f;
+#pragma unroll
+      for (int pi = 0; pi < CI_PIX; ++pi) acc[pi] = bv;
+      for (int k = 0; k < K; ++k) {
+        const float wv = ws[k * Cout + co];
+#pragma unroll
+        for (int pi = 0; pi < CI_PIX; ++pi) acc[pi] = fmaf(patch[pi * K + k], wv, acc[pi]);
+      }
+#pragma unroll
+      for (int pi = 0; pi < CI_PIX; ++pi) if (p0 + pi < pixels) out[(p0 + pi) * Cout + co] = from_f<T>(acc[pi]);
+    }
+  }
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = from_f<D>(to_f(s[i]));
+}
+
+}  // namespace mmg
+
+using namespace mmg;
+
+extern "C" int mmg_layernorm(const mmg_layernorm_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MMG_CHECK_ARG(a && a->x && a->y && a->gamma, "mmg_layernorm: NULL pointer");
+  MMG_CHECK_ARG(a->width > 0 && a->width <= LN_MAXV * 128, "mmg_layernorm: width %lld not in (0, %d]", (long long)a->width, LN_MAXV * 128);
+  MMG_CHECK_ARG(a->ldy >= a->width && a->ldx >= a->width, "mmg_layernorm: leading dims");
+  MMG_CHECK_ARG(!a->x_out || a->x_dtype == MMG_F32, "mmg_layernorm: x_out requires fp32 x");
+  if (a->rows == 0) return MMG_OK;
+  const unsigned grid = (unsigned)((a->rows + 7) / 8);
+  const int w = (int)a->width;
+#define LN_LAUNCH(TX, TY) layernorm_kernel<TX, TY><<<grid, 256, 0, st>>>((const TX*)a->x, (TY*)a->y, a->gamma, a->add, a->x_out, a->rows, w, a->ldx, a->ldy)
+  if (a->x_dtype == MMG_F32 && a->y_dtype == MMG_F32) LN_LAUNCH(float, float);
+  else if (a->x_dtype == MMG_F32 && a->y_dtype == MMG_BF16) LN_LAUNCH(float, bf16);
+  else if (a->x_dtype == MMG_BF16 && a->y_dtype == MMG_BF16) LN_LAUNCH(bf16, bf16);
+  else return fail(MMG_EINVAL, "mmg_layernorm: unsupported dtype pair %d -> %d", a->x_dtype, a->y_dtype);
+#undef LN_LAUNCH
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
+extern "C" int mmg_embed(const mmg_embed_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MMG_CHECK_ARG(a && a->ids && a->token_emb && a->x && (a->pos_emb || !a->use_pos), "mmg_embed: NULL pointer");
+  MMG_CHECK_ARG(a->dim % 4 == 0 && a->copies >= 1 && a->n > 0, "mmg_embed: dim %% 4, copies, n");
+  if (a->rows == 0) return MMG_OK;
+  embed_kernel<<<(unsigned)a->rows, 128, 0, st>>>(a->ids, a->token_emb, a->use_pos ? a->pos_emb : a->token_emb, a->x, a->rows, a->n, a->dim, a->copies, a->use_pos);
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
+extern "C" int mmg_final_embed(const mmg_final_embed_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MMG_CHECK_ARG(a && a->x_cond && a->gamma && a->masked_pos && a->e, "mmg_final_embed: NULL pointer");
+  MMG_CHECK_ARG(a->dim > 0 && a->dim <= LN_MAXV * 128, "mmg_final_embed: dim");
+  const int64_t R = (int64_t)a->B * a->num_masked;
+  if (R == 0) return MMG_OK;
+  const unsigned grid = (unsigned)((R + 7) / 8);
+  if (a->e_dtype == MMG_BF16) final_embed_kernel<bf16><<<grid, 256, 0, st>>>(a->x_cond, a->x_null, a->gamma, a->masked_pos, (bf16*)a->e, a->B, a->n, a->num_masked, a->dim, a->cond_scale);
+  else final_embed_kernel<float><<<grid, 256, 0, st>>>(a->x_cond, a->x_null, a->gamma, a->masked_pos, (float*)a->e, a->B, a->n, a->num_masked, a->dim, a->cond_scale);
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
+extern "C" int mmg_groupnorm(const mmg_groupnorm_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MMG_CHECK_ARG(a && a->x && a->gamma && a->beta, "mmg_groupnorm: NULL pointer");
+  MMG_CHECK_ARG(a->groups > 0 && a->C % a->groups == 0, "mmg_groupnorm: C %% groups");
+  const unsigned grid = (unsigned)(a->B * a->groups);
+  if (a->dtype == MMG_BF16) groupnorm_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)a->x, a->gamma, a->beta, a->HW, a->C, a->groups, a->act);
+  else groupnorm_kernel<float><<<grid, 256, 0, st>>>((float*)a->x, a->gamma, a->beta, a->HW, a->C, a->groups, a->act);
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
+extern "C" int mmg_conv_in(const mmg_conv_in_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MMG_CHECK_ARG(a && a->img && a->w && a->out, "mmg_conv_in: NULL pointer");
+  MMG_CHECK_ARG(a->C >= 1 && a->C <= 4, "mmg_conv_in: channels %d not in [1,4]", a->C);
+  const size_t smem = ((size_t)a->Cout + CI_PIX) * a->C * 25 * sizeof(float);
+  MMG_CHECK_ARG(smem <= 200 * 1024, "mmg_conv_in: Cout too large");
+  int64_t pixels = ((int64_t)a->B * a->H * a->W + CI_PIX - 1) / CI_PIX;
+  if (pixels > (int64_t)num_sms() * 2) pixels = (int64_t)num_sms() * 2;
+  if (a->out_dtype == MMG_BF16) {
+    MMG_CUDA(cudaFuncSetAttribute(conv_in_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_in_kernel<bf16><<<(unsigned)pixels, 256, smem, st>>>(a->img, a->w, a->bias, (bf16*)a->out, a->B, a->C, a->H, a->W, a->Cout);
+  } else {
+    MMG_CUDA(cudaFuncSetAttribute(conv_in_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_in_kernel<float><<<(unsigned)pixels, 256, smem, st>>>(a->img, a->w, a->bias, (float*)a->out, a->B, a->C, a->H, a->W, a->Cout);
+  }
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
+extern "C" int mmg_cast(const mmg_cast_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MMG_CHECK_ARG(a && a->src && a->dst, "mmg_cast: NULL pointer");
+  if (a->n == 0) return MMG_OK;
+  const unsigned grid = (unsigned)((a->n + 255) / 256 < 148 * 16 ? (a->n + 255) / 256 : 148 * 16);
+  if (a->src_dtype == MMG_F32 && a->dst_dtype == MMG_BF16) cast_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)a->src, (bf16*)a->dst, a->n);
+  else if (a->src_dtype == MMG_BF16 && a->dst_dtype == MMG_F32) cast_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)a->src, (float*)a->dst, a->n);
+  else return fail(MMG_EINVAL, "mmg_cast: unsupported dtype pair");
+  MMG_LAUNCHED();
+  return MMG_OK;
+}

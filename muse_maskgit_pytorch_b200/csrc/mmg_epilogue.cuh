@@ -1,0 +1,216 @@
+// Fused GEMM epilogues, shared by the tcgen05 kernel (mmg_gemm_tc.cu) and the fp32 CUDA-core kernel
+// (mmg_gemm_simt.cu).  One thread owns one output row and walks it in chunks of 64 accumulator columns.
+#pragma once
+#include "mmg_common.cuh"
+
+namespace mmg {
+
+struct Epilogue {
+  mmg_epilogue_args p;
+  int kind;
+  int64_t M, N;
+  float rgb_acc[4];
+
+  template <typename T>
+  static __device__ __forceinline__ void store_n(T* dst, const float* v, int n, bool vec_ok) {
+    if (vec_ok && n == 64) {
+      float t[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) t[i] = v[i];
+      Vec64<T>::store(dst, t);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) if (i < n) dst[i] = from_f<T>(v[i]);
+    }
+  }
+  static __device__ __forceinline__ void store32_bf16(bf16* dst, const float* v) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 t;
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), b = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+      __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), d = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+      t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+      t.z = *reinterpret_cast<uint32_t*>(&c); t.w = *reinterpret_cast<uint32_t*>(&d);
+      reinterpret_cast<uint4*>(dst)[i] = t;
+    }
+  }
+
+  __device__ __forceinline__ void begin_row(int64_t) {
+    if (kind == MMG_EPI_CONVT_RGB) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rgb_acc[c] = (c < p.rgb_channels) ? p.rgb_b[c] : 0.f;
+    }
+  }
+
+  // row: global output row (< M). col0: first accumulator column of this chunk (multiple of 64). nvalid: columns < N.
+  __device__ __forceinline__ void apply(int64_t row, int col0, float (&v)[64], int nvalid) {
+    const bool bf = (p.out_dtype == MMG_BF16);
+    switch (kind) {
+      case MMG_EPI_STORE:
+      case MMG_EPI_RESIDUAL: {
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) if (i < nvalid) v[i] += __ldg(p.bias + col0 + i);
+        }
+        const bool vec_ok = (nvalid == 64) && ((p.ldo & 7) == 0);
+        if (kind == MMG_EPI_RESIDUAL) {
+          const bool rvec = vec_ok && ((p.ldr & 7) == 0);
+          if (bf) {
+            const bf16* r = reinterpret_cast<const bf16*>(p.resid) + row * p.ldr + col0;
+            if (rvec) { float t[64]; Vec64<bf16>::load(r, t);
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] += t[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 64; ++i) if (i < nvalid) v[i] += to_f(r[i]);
+            }
+          } else {
+            const float* r = reinterpret_cast<const float*>(p.resid) + row * p.ldr + col0;
+            if (rvec) { float t[64]; Vec64<float>::load(r, t);
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] += t[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 64; ++i) if (i < nvalid) v[i] += r[i];
+            }
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = leaky01(v[i]);
+        }
+        if (bf) store_n(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col0, v, nvalid, vec_ok);
+        else    store_n(reinterpret_cast<float*>(p.out) + row * p.ldo + col0, v, nvalid, vec_ok);
+        break;
+      }
+      case MMG_EPI_GEGLU:
+      case MMG_EPI_GLU: {
+        float o[32];
+        if (kind == MMG_EPI_GEGLU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = v[32 + i] * gelu_erf(v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = v[i] + (p.bias ? __ldg(p.bias + col0 + i) : 0.f);
+            float g = v[32 + i] + (p.bias ? __ldg(p.bias + col0 + 32 + i) : 0.f);
+            o[i] = a * (1.0f / (1.0f + expf(-g)));
+          }
+        }
+        const int oc = col0 >> 1;
+        if (bf) {
+          bf16* d = reinterpret_cast<bf16*>(p.out) + row * p.ldo + oc;
+          if ((p.ldo & 7) == 0) store32_bf16(d, o);
+          else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d[i] = from_f<bf16>(o[i]);
+          }
+        } else {
+          float* d = reinterpret_cast<float*>(p.out) + row * p.ldo + oc;
+          if ((p.ldo & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(d)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d[i] = o[i];
+          }
+        }
+        break;
+      }
+      case MMG_EPI_QKV: {
+        const int hc = col0 >> 6;
+        const int64_t b = row / p.tokens, t = row - b * p.tokens;
+        void* dst; int h; int64_t off;
+        const float* sc = nullptr;
+        if (hc < p.nq_heads) { h = hc; dst = p.q_out; off = ((b * p.heads + h) * (int64_t)p.q_rows + t) * 64; sc = p.q_scale; }
+        else if (hc < p.nq_heads + p.nk_heads) { h = hc - p.nq_heads; dst = p.k_out; off = ((b * p.heads + h) * (int64_t)p.kv_rows + p.key_off + t) * 64; sc = p.k_scale; }
+        else { h = hc - p.nq_heads - p.nk_heads; dst = p.v_out; off = ((b * p.heads + h) * (int64_t)p.kv_rows + p.key_off + t) * 64; }
+        if (sc) {  // F.normalize(dim=-1, eps=1e-12) then * scale   (muse_maskgit_pytorch.py:151-153)
+          float ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) ss += v[i] * v[i];
+          const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = v[i] * inv * __ldg(sc + i);
+        }
+        if (bf) Vec64<bf16>::store(reinterpret_cast<bf16*>(dst) + off, v);
+        else    Vec64<float>::store(reinterpret_cast<float*>(dst) + off, v);
+        if (t == 0 && hc >= p.nq_heads) {              // learned null key / value -> key row 0 (muse_maskgit_pytorch.py:145-149)
+          const void* nsrc = (hc < p.nq_heads + p.nk_heads) ? p.null_k : p.null_v;
+          if (nsrc) {
+            const int64_t noff = ((b * p.heads + h) * (int64_t)p.kv_rows) * 64;
+            if (bf) {
+              const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(nsrc) + h * 64);
+              uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(dst) + noff);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dp[i] = sp[i];
+            } else {
+              const float4* sp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(nsrc) + h * 64);
+              float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + noff);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) dp[i] = sp[i];
+            }
+          }
+        }
+        break;
+      }
+      case MMG_EPI_CONVT:
+      case MMG_EPI_CONVT_RGB: {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = leaky01(v[i] + (p.bias ? __ldg(p.bias + col0 + i) : 0.f));
+        if (kind == MMG_EPI_CONVT) {
+          const int64_t hw = (int64_t)p.H * p.W;
+          const int64_t b = row / hw; const int rem = (int)(row - b * hw); const int y = rem / p.W, x = rem - y * p.W;
+          const int64_t opix = (b * 2 * p.H + 2 * y + p.py) * (int64_t)(2 * p.W) + 2 * x + p.px;
+          const bool vec_ok = (nvalid == 64) && ((p.ldo & 7) == 0);
+          if (bf) store_n(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + col0, v, nvalid, vec_ok);
+          else    store_n(reinterpret_cast<float*>(p.out) + opix * p.ldo + col0, v, nvalid, vec_ok);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < p.rgb_channels) {
+              const float* w = p.rgb_w + (int64_t)c * N + col0;
+              float s = 0.f;
+#pragma unroll
+              for (int i = 0; i < 64; ++i) if (i < nvalid) s += v[i] * __ldg(w + i);
+              rgb_acc[c] += s;
+            }
+          }
+        }
+        break;
+      }
+    }
+  }
+
+  __device__ __forceinline__ void end_row(int64_t row) {
+    if (kind == MMG_EPI_CONVT_RGB) {
+      const int64_t hw = (int64_t)p.H * p.W;
+      const int64_t b = row / hw; const int rem = (int)(row - b * hw); const int y = rem / p.W, x = rem - y * p.W;
+      const int oy = 2 * y + p.py, ox = 2 * x + p.px;
+      float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < p.rgb_channels) o[((b * p.rgb_channels + c) * (int64_t)(2 * p.H) + oy) * (2 * p.W) + ox] = rgb_acc[c];
+    }
+  }
+};
+
+// host-side validation shared by the launchers
+inline int validate_epilogue(int kind, const mmg_epilogue_args& e, int64_t N) {
+  switch (kind) {
+    case MMG_EPI_STORE: MMG_CHECK_ARG(e.out, "epilogue STORE: out is NULL"); break;
+    case MMG_EPI_RESIDUAL: MMG_CHECK_ARG(e.out && e.resid, "epilogue RESIDUAL: out/resid NULL"); break;
+    case MMG_EPI_GEGLU: case MMG_EPI_GLU: MMG_CHECK_ARG(e.out && (N % 64) == 0, "epilogue GEGLU/GLU: N %% 64 != 0 or out NULL"); break;
+    case MMG_EPI_QKV:
+      MMG_CHECK_ARG((N % 64) == 0 && N / 64 == e.nq_heads + e.nk_heads + e.nv_heads, "epilogue QKV: N != 64*(nq+nk+nv)");
+      MMG_CHECK_ARG(e.tokens > 0 && e.heads > 0, "epilogue QKV: tokens/heads");
+      MMG_CHECK_ARG((!e.nq_heads || (e.q_out && e.q_scale)) && (!e.nk_heads || (e.k_out && e.k_scale)) && (!e.nv_heads || e.v_out), "epilogue QKV: NULL output");
+      break;
+    case MMG_EPI_CONVT: MMG_CHECK_ARG(e.out && e.H > 0 && e.W > 0, "epilogue CONVT: geometry"); break;
+    case MMG_EPI_CONVT_RGB: MMG_CHECK_ARG(e.out && e.rgb_w && e.rgb_b && e.rgb_channels >= 1 && e.rgb_channels <= 4, "epilogue CONVT_RGB: args"); break;
+    default: return fail(MMG_EINVAL, "unknown epilogue %d", kind);
+  }
+  return MMG_OK;
+}
+
+}  // namespace mmg

@@ -1,0 +1,175 @@
+// tcgen05 / TMA / TMEM GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T, bf16 operands, fp32 accumulation in TMEM.
+//
+//   warp 0      : TMA producer  (one elected lane) — A tile 128x64 and W tile BNx64 per k-block, SWIZZLE_128B
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane) — 4 x tcgen05.mma (K=16) per k-block, M=128, N=BN
+//   warps 2..5  : epilogue — tcgen05.ld (32 lanes x 32 cols) -> registers -> fused Epilogue -> global
+//   persistent grid (<= #SM CTAs), static tile schedule, STAGES-deep smem ring, 2 accumulator stages in TMEM so the
+//   epilogue of tile i overlaps the main loop of tile i+1.
+//
+// A is either a dense [M,K] matrix (2-D tensor map) or an NHWC activation addressed as an implicit-GEMM
+// convolution: the k-block (tap, channel-chunk) is fetched with a 4-D tensor map at shifted (x+dx, y+dy)
+// coordinates and TMA's out-of-bounds zero fill provides the padding — no im2col buffer.
+#pragma once
+#include "mmg_common.cuh"
+#include "mmg_sm100.cuh"
+#include "mmg_epilogue.cuh"
+
+namespace mmg {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_TAPS = 16;
+
+struct alignas(64) TcGemmParams {
+  CUtensorMap tma_a[4];
+  CUtensorMap tma_b;
+  int64_t M, N;
+  int num_kb, num_m_tiles, num_n_tiles;
+  int mode;                 // 0 dense, 1 conv (4-D A maps)
+  int cchunks, ntaps;       // conv: k-block = tap * cchunks + channel chunk
+  int8_t tap_map[TC_MAX_TAPS], tap_dy[TC_MAX_TAPS], tap_dx[TC_MAX_TAPS];
+  int TW, TH, TB, tiles_x, tiles_y;   // conv: tile = TB images x TH rows x TW cols of the OUTPUT grid (Ho x Wo)
+  int Ho, Wo, B;
+  Epilogue epi;
+};
+
+template <int BN> struct TcCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+  using namespace sm100;
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tma_b);
+    prefetch_tmap(&p.tma_a[0]);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.num_m_tiles, n_blk = tile / p.num_m_tiles;
+        int x0 = 0, y0 = 0, b0 = 0;
+        if (p.mode == 1) {
+          const int xt = m_blk % p.tiles_x, yt = (m_blk / p.tiles_x) % p.tiles_y, bt = m_blk / (p.tiles_x * p.tiles_y);
+          x0 = xt * p.TW; y0 = yt * p.TH; b0 = bt * p.TB;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(full_bar + stage, Cfg::STAGE_BYTES);
+          if (p.mode == 0) {
+            tma_load_2d(sa, &p.tma_a[0], full_bar + stage, kb * TC_BK, m_blk * TC_BM);
+          } else {
+            const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+            tma_load_4d(sa, &p.tma_a[p.tap_map[tap]], full_bar + stage, cc * TC_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
+          }
+          tma_load_2d(sb, &p.tma_b, full_bar + stage, kb * TC_BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = idesc_bf16_f32(TC_BM, BN, false, false);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(full_bar + stage, phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = smem_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = smem_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar + stage);                         // smem slot free once these MMAs retire
+          if (kb == p.num_kb - 1) umma_commit(tmem_full + acc);   // accumulator ready for the epilogue
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r_in_tile = quarter * 32 + lane;
+    Epilogue epi = p.epi;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m_tiles, n_blk = tile / p.num_m_tiles;
+      int64_t row; bool valid;
+      if (p.mode == 0) {
+        row = (int64_t)m_blk * TC_BM + r_in_tile; valid = row < p.M;
+      } else {
+        const int xt = m_blk % p.tiles_x, yt = (m_blk / p.tiles_x) % p.tiles_y, bt = m_blk / (p.tiles_x * p.tiles_y);
+        const int tx = r_in_tile % p.TW, ty = (r_in_tile / p.TW) % p.TH, tb = r_in_tile / (p.TW * p.TH);
+        const int b = bt * p.TB + tb;
+        valid = b < p.B;
+        row = ((int64_t)b * p.Ho + (yt * p.TH + ty)) * p.Wo + xt * p.TW + tx;
+      }
+      mbar_wait(tmem_full + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      if (valid) epi.begin_row(row);
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        float v[64];
+        tmem_ld_32x32b_x32(t_row + c * 64, v);
+        tmem_ld_32x32b_x32(t_row + c * 64 + 32, v + 32);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 64;
+        if (valid && col0 < p.N) epi.apply(row, col0, v, 64);
+      }
+      if (valid) epi.end_row(row);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
+}
+
+}  // namespace mmg

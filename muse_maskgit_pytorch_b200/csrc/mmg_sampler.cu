@@ -1,0 +1,354 @@
+// Sampler kernels for MaskGit.generate(): re-mask and the fused top-k / gumbel-argmax / confidence tail.
+//
+// mmg_logits_sample reads every logits row from HBM exactly once (the algorithmic minimum once logits are
+// materialised: 4 B / logit).  Per row (one 512-thread CTA):
+//   A. a 4096-element strided sample (128 lines of 128 B) gives a provisional threshold t_lo whose expected
+//      exceedance count is ~k + 4.5 sigma;
+//   B. one streaming pass (128-bit loads, L1 no-allocate): online softmax statistics (max, sum exp) and the
+//      candidates {x >= t_lo} appended to a shared-memory list with one atomic per warp-iteration;
+//   C. on the list only (~1.2 k entries): gumbel noise (2 logs per candidate instead of per logit), block argmax of
+//      the perturbed value, accepted iff the candidate's exact rank (#greater + #equal-with-lower-index) is < k,
+//      else excluded and repeated.  This equals argmax over torch.topk's kept set without ever forming the set.
+//   If the list would miss the top-k (count < k) or overflow, an exact bitwise radix descent over the L2-resident
+//   row finds the k-th largest key and the list is rebuilt (rare; exercised by the tests with adversarial rows).
+#include "mmg_common.cuh"
+#include <float.h>
+
+namespace mmg {
+
+constexpr int SMP_THREADS = 512;
+constexpr int SMP_SAMPLE = 4096;
+constexpr int SMP_CAP = 9216;
+
+__device__ __forceinline__ uint32_t fkey(float x) {           // order-preserving float -> uint32
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+  float4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return v;
+}
+
+// Philox4x32-10, counter = (v, step, row_lo, row_hi), key = seed; returns the first output word.
+__device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+
+struct ArgBest { float val; int idx; };          // idx: list slot (for exclusion) ; tie -> lowest vocabulary index
+__device__ __forceinline__ bool better(float v, int vi, float w, int wi) { return v > w || (v == w && vi < wi); }
+
+__global__ void __launch_bounds__(SMP_THREADS)
+logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
+  extern __shared__ uint8_t smraw[];
+  float* lval = reinterpret_cast<float*>(smraw);                 // [SMP_CAP]
+  int* lidx = reinterpret_cast<int*>(lval + SMP_CAP);            // [SMP_CAP]
+  float* samp = reinterpret_cast<float*>(lidx + SMP_CAP);        // [SMP_SAMPLE]  (reused as perturbed values in phase C)
+  __shared__ int s_count, s_n;
+  __shared__ float s_redf[32]; __shared__ int s_redi[32]; __shared__ int s_redj[32];
+  __shared__ float s_max, s_sum, s_tlo;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = a.V, k = a.k;
+  const int64_t r = blockIdx.x;
+  const int b = (int)(r / a.num_masked);
+  const int pos = a.masked_pos[r];
+  const float* row = a.logits + r * (int64_t)V;
+
+  // ---------------- phase A: sample -> provisional threshold ----------------
+  const int ns = V < SMP_SAMPLE ? V : SMP_SAMPLE;
+  {
+    // 32-element lines spread evenly over the row
+    const int nlines = ns / 32, vlines = V / 32;
+    for (int i = tid; i < ns; i += SMP_THREADS) {
+      int src;
+      if (ns == V) src = i; else { const int ln = i >> 5; src = (int)(((int64_t)ln * vlines) / nlines) * 32 + (i & 31); }
+      samp[i] = row[src];
+    }
+  }
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  float tlo;
+  {
+    // rank of the provisional threshold inside the sample
+    int rs;
+    if (ns == V) rs = k;
+    else { const float pf = (float)k / (float)V; const float mu = pf * ns; rs = (int)(mu + 4.5f * sqrtf(mu * (1.f - pf)) + 2.f); }
+    if (rs > ns) rs = ns;
+    // bitwise radix descent on the sample keys: largest key t with count(key >= t) >= rs  == rs-th largest sample
+    uint32_t prefix = 0;
+    for (int bit = 31; bit >= (ns == V ? 0 : 12); --bit) {   // sampled rows: 20 key bits are enough for a lower bound
+      const uint32_t cand = prefix | (1u << bit);
+      int c = 0;
+      for (int i = tid; i < ns; i += SMP_THREADS) c += (fkey(samp[i]) >= cand);
+      c = __reduce_add_sync(0xffffffffu, c);
+      __syncthreads();
+      if (lane == 0) s_redi[warp] = c;
+      __syncthreads();
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < SMP_THREADS / 32; ++w) tot += s_redi[w];
+      if (tot >= rs) prefix = cand;
+    }
+    const uint32_t u = (prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix;
+    tlo = __uint_as_float(u);
+  }
+
+  // ---------------- phase B: one streaming pass ----------------
+  float m_t = -FLT_MAX, s_t = 0.f;
+  auto visit = [&](float x) {
+    if (x > m_t) { s_t = s_t * expf(m_t - x) + 1.f; m_t = x; } else { s_t += expf(x - m_t); }
+  };
+  auto append = [&](const bool* f, const float* xs, int base) {   // warp-aggregated append of this lane's flagged candidates
+    const int c = (int)f[0] + (int)f[1] + (int)f[2] + (int)f[3];
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    if (tot == 0) return;
+    int start = 0;
+    if (lane == 0) start = atomicAdd(&s_count, tot);
+    start = __shfl_sync(0xffffffffu, start, 0) + incl - c;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (f[j]) { if (start < SMP_CAP) { lval[start] = xs[j]; lidx[start] = base + j; } ++start; }
+  };
+  if ((V & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const int n4 = V >> 2;
+    for (int i0 = 0; i0 < n4; i0 += SMP_THREADS) {
+      const int i = i0 + tid;
+      float xs[4] = {0.f, 0.f, 0.f, 0.f}; bool f[4] = {false, false, false, false};
+      if (i < n4) {
+        const float4 q = ld_stream4(r4 + i);
+        xs[0] = q.x; xs[1] = q.y; xs[2] = q.z; xs[3] = q.w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { visit(xs[j]); f[j] = (xs[j] >= tlo); }
+      }
+      append(f, xs, i * 4);
+    }
+  } else {
+    for (int i0 = 0; i0 < V; i0 += SMP_THREADS) {
+      const int i = i0 + tid;
+      float xs[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX}; int c = 0;
+      if (i < V) { xs[0] = ld_stream(row + i); visit(xs[0]); c = (xs[0] >= tlo); }
+      // lanes hold one element each: positions base+0 only
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const int tot = __shfl_sync(0xffffffffu, incl, 31);
+      if (tot) {
+        int start = 0;
+        if (lane == 0) start = atomicAdd(&s_count, tot);
+        start = __shfl_sync(0xffffffffu, start, 0) + incl - c;
+        if (c && start < SMP_CAP) { lval[start] = xs[0]; lidx[start] = i; }
+      }
+    }
+  }
+  // block softmax statistics
+  {
+    float m = warp_max(m_t);
+    if (lane == 0) s_redf[warp] = m;
+    __syncthreads();
+    float M = s_redf[lane % (SMP_THREADS / 32)];
+    M = warp_max(M);
+    float s = s_t * expf(m_t - M);
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) s_redf[warp] = s;
+    __syncthreads();
+    if (tid == 0) { float t = 0.f; for (int w = 0; w < SMP_THREADS / 32; ++w) t += s_redf[w]; s_sum = t; s_max = M; s_n = s_count; }
+    __syncthreads();
+  }
+  int n = s_n;
+
+  // ---------------- rare: exact rebuild when the sample threshold missed ----------------
+  if (n < k || n > SMP_CAP) {
+    // k-th largest key of the row by bitwise descent (row is L2 resident now)
+    uint32_t prefix = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
+      int c = 0;
+      for (int i = tid; i < V; i += SMP_THREADS) c += (fkey(row[i]) >= cand);
+      c = __reduce_add_sync(0xffffffffu, c);
+      __syncthreads();
+      if (lane == 0) s_redi[warp] = c;
+      __syncthreads();
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < SMP_THREADS / 32; ++w) tot += s_redi[w];
+      if (tot >= k) prefix = cand;
+    }
+    // list = all keys > prefix (fewer than k of them), then ties (== prefix) in index order until k entries
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < V; i0 += SMP_THREADS) {
+      const int i = i0 + tid;
+      const float x = i < V ? row[i] : 0.f;
+      const bool in = i < V && fkey(x) > prefix;
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      int start = 0;
+      if (lane == 0 && bal) start = atomicAdd(&s_count, __popc(bal));
+      start = __shfl_sync(0xffffffffu, start, 0) + __popc(bal & ((1u << lane) - 1));
+      if (in) { lval[start] = x; lidx[start] = i; }
+    }
+    __syncthreads();
+    if (warp == 0) {             // ties, serial in index order (one warp), lowest indices first
+      int cnt = s_count;
+      for (int i0 = 0; i0 < V && cnt < k; i0 += 32) {
+        const int i = i0 + lane;
+        const float x = i < V ? row[i] : 0.f;
+        const bool tie = i < V && fkey(x) == prefix;
+        const unsigned bal = __ballot_sync(0xffffffffu, tie);
+        const int slot = cnt + __popc(bal & ((1u << lane) - 1));
+        if (tie && slot < k) { lval[slot] = x; lidx[slot] = i; }
+        cnt += __popc(bal);
+      }
+      if (lane == 0) s_n = cnt < k ? cnt : k;
+    }
+    __syncthreads();
+    n = s_n;
+  }
+
+  // ---------------- phase C: perturbed argmax restricted to the exact top-k ----------------
+  const int64_t grow = a.row_offset + (int64_t)b * a.n + pos;
+  constexpr int PER = (SMP_CAP + SMP_THREADS - 1) / SMP_THREADS;
+  float pv[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int s = tid + j * SMP_THREADS;
+    float p = -FLT_MAX;
+    if (s < n) {
+      const int v = lidx[s];
+      float u;
+      if (a.u) u = a.u[((int64_t)b * a.n + pos) * V + v];
+      else u = (float)(philox_first((uint32_t)v, (uint32_t)a.step, (uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32)) >> 8) * (1.0f / 16777216.0f);
+      const float l1 = logf(fmaxf(u, 1e-20f));
+      const float g = -logf(fmaxf(-l1, 1e-20f));
+      p = __fdiv_rn(lval[s], tdiv) + g;
+    }
+    pv[j] = p;
+  }
+  int win_v = -1; float win_x = 0.f;
+  for (int iter = 0; iter < n; ++iter) {
+    // block argmax of perturbed value (ties -> lowest vocabulary index)
+    float bv = -FLT_MAX; int bi = 0x7fffffff, bs = -1;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int s = tid + j * SMP_THREADS;
+      if (s < n) { const int vi = lidx[s]; if (bs < 0 || better(pv[j], vi, bv, bi)) { bv = pv[j]; bi = vi; bs = s; } }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o); const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+      if (os >= 0 && (bs < 0 || better(ov, oi, bv, bi))) { bv = ov; bi = oi; bs = os; }
+    }
+    __syncthreads();
+    if (lane == 0) { s_redf[warp] = bv; s_redi[warp] = bi; s_redj[warp] = bs; }
+    __syncthreads();
+    bv = s_redf[0]; bi = s_redi[0]; bs = s_redj[0];
+#pragma unroll
+    for (int w = 1; w < SMP_THREADS / 32; ++w) {
+      const float ov = s_redf[w]; const int oi = s_redi[w], os = s_redj[w];
+      if (os >= 0 && (bs < 0 || better(ov, oi, bv, bi))) { bv = ov; bi = oi; bs = os; }
+    }
+    // exact rank of the candidate inside the row (list covers everything >= its value)
+    const float cx = lval[bs];
+    int c = 0;
+    for (int s = tid; s < n; s += SMP_THREADS) { const float x = lval[s]; c += (x > cx) || (x == cx && lidx[s] < bi); }
+    c = __reduce_add_sync(0xffffffffu, c);
+    __syncthreads();
+    if (lane == 0) s_redi[warp] = c;
+    __syncthreads();
+    int rank = 0;
+#pragma unroll
+    for (int w = 0; w < SMP_THREADS / 32; ++w) rank += s_redi[w];
+    if (rank < k) { win_v = bi; win_x = cx; break; }
+    // not in the top-k: exclude and retry
+    // not in the kept set: drop its perturbed value (its logit stays in the list for later rank computations)
+#pragma unroll
+    for (int j = 0; j < PER; ++j) if (tid + j * SMP_THREADS == bs) pv[j] = -FLT_MAX;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (win_v < 0) { win_v = 0; win_x = row[0]; }                 // degenerate rows (all -inf / NaN)
+    const float p = expf(win_x - s_max) / s_sum;
+    a.ids[(int64_t)b * a.n + pos] = win_v;
+    a.scores[(int64_t)b * a.n + pos] = 1.0f - p;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// re-mask: per batch row pick the num_masked largest scores (ties: lowest position), scatter mask_id, reset scores.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+remask_kernel(int64_t* __restrict__ ids, float* __restrict__ scores, int32_t* __restrict__ masked_pos, int n, int num_masked, int64_t mask_id) {
+  extern __shared__ float sc[];                       // [n] scores, then [n] flags (as int)
+  int* flag = reinterpret_cast<int*>(sc + n);
+  __shared__ int woff[9];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < n; i += 256) sc[i] = scores[(int64_t)b * n + i];
+  __syncthreads();
+  for (int i = tid; i < n; i += 256) {
+    const float s = sc[i]; int rank = 0;
+    for (int j = 0; j < n; ++j) { const float t = sc[j]; rank += (t > s) || (t == s && j < i); }
+    flag[i] = rank < num_masked;
+  }
+  __syncthreads();
+  // ordered compaction: each thread owns a contiguous chunk
+  const int per = (n + 255) / 256, lo = tid * per, hi = min(n, lo + per);
+  int c = 0;
+  for (int i = lo; i < hi; ++i) c += flag[i];
+  int incl = c;
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) woff[warp + 1] = incl;
+  if (tid == 0) woff[0] = 0;
+  __syncthreads();
+  if (tid == 0) for (int w = 1; w <= 8; ++w) woff[w] += woff[w - 1];
+  __syncthreads();
+  int o = woff[warp] + incl - c;
+  for (int i = lo; i < hi; ++i) {
+    if (flag[i]) { masked_pos[(int64_t)b * num_masked + o++] = i; ids[(int64_t)b * n + i] = mask_id; }
+    scores[(int64_t)b * n + i] = -1e5f;
+  }
+}
+
+}  // namespace mmg
+
+using namespace mmg;
+
+extern "C" int mmg_logits_sample(const mmg_logits_sample_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MMG_CHECK_ARG(a && a->logits && a->masked_pos && a->ids && a->scores, "mmg_logits_sample: NULL pointer");
+  MMG_CHECK_ARG(a->V >= 32 && a->V % 32 == 0, "mmg_logits_sample: V=%d must be a positive multiple of 32", a->V);
+  MMG_CHECK_ARG(a->k >= 1 && a->k <= a->V && a->k <= SMP_CAP, "mmg_logits_sample: k=%d out of range (<= %d)", a->k, SMP_CAP);
+  const int64_t R = (int64_t)a->B * a->num_masked;
+  if (R == 0) return MMG_OK;
+  static const size_t smem = (size_t)SMP_CAP * 8 + (size_t)SMP_SAMPLE * 4;
+  static cudaError_t attr = cudaFuncSetAttribute(logits_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (attr != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(logits_sample): %s", cudaGetErrorString(attr));
+  float t = a->temperature; if (t < 1e-10f) t = 1e-10f;      // max(temperature, 1e-10): muse_maskgit_pytorch.py:411
+  logits_sample_kernel<<<(unsigned)R, SMP_THREADS, smem, st>>>(*a, t);
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
+extern "C" int mmg_remask(const mmg_remask_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MMG_CHECK_ARG(a && a->ids && a->scores && a->masked_pos, "mmg_remask: NULL pointer");
+  MMG_CHECK_ARG(a->n > 0 && a->num_masked >= 1 && a->num_masked <= a->n && a->n <= 16384, "mmg_remask: n=%d num_masked=%d", a->n, a->num_masked);
+  if (a->B == 0) return MMG_OK;
+  remask_kernel<<<a->B, 256, (size_t)a->n * 8, st>>>(a->ids, a->scores, a->masked_pos, a->n, a->num_masked, a->mask_id);
+  MMG_LAUNCHED();
+  return MMG_OK;
+}

@@ -1,0 +1,482 @@
+"""Transformer / MaskGitTransformer / TokenCritic / MaskGit / Muse — host-side mirror of the reference classes
+(ref: muse_maskgit_pytorch.py:199-386, 427-791) over libmmg.so.
+
+The nn.Modules here only HOLD parameters under the reference's state_dict keys; the arithmetic of
+`forward`, `forward_with_cond_scale` and `MaskGit.generate` is issued as sm_100a kernels through the C-ABI:
+  tcgen05 GEMMs with fused epilogues (QKV split + l2norm/scale, residual, GEGLU), tcgen05 attention, LayerNorm,
+  the masked-row final-LN + CFG combine, the logits GEMM on masked rows only, and the fused sampling tail.
+Both CFG branches of a decode step run as one batch of 2B sequences; the null branch's cross-attention is the
+constant to_out(null_v) (every text key masked -> softmax puts weight exactly 1 on the null key).
+"""
+import math
+from functools import partial
+from pathlib import Path
+from typing import Callable, List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .t5 import t5_encode_text, get_encoded_dim, DEFAULT_T5_NAME
+from .vqgan_vae import VQGanVAE
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------ parameter holders
+class LayerNorm(nn.Module):
+    """gamma parameter + zero `beta` buffer (ref: muse_maskgit_pytorch.py:63-67)."""
+    def __init__(self, dim):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(dim))
+        self.register_buffer("beta", torch.zeros(dim))
+
+
+def _ff_params(dim, mult=4):
+    inner = int(dim * mult * 2 / 3)                       # ref: muse_maskgit_pytorch.py:82
+    return nn.Sequential(LayerNorm(dim), nn.Linear(dim, inner * 2, bias=False), nn.Identity(), LayerNorm(inner),
+                         nn.Linear(inner, dim, bias=False))
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, dim_head=64, heads=8, cross_attend=False, scale=8):
+        super().__init__()
+        inner = dim_head * heads
+        self.scale, self.heads, self.cross_attend = scale, heads, cross_attend
+        self.norm = LayerNorm(dim)
+        self.null_kv = nn.Parameter(torch.randn(2, heads, 1, dim_head))
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_kv = nn.Linear(dim, inner * 2, bias=False)
+        self.q_scale = nn.Parameter(torch.ones(dim_head))
+        self.k_scale = nn.Parameter(torch.ones(dim_head))
+        self.to_out = nn.Linear(inner, dim, bias=False)
+
+
+class TransformerBlocks(nn.Module):
+    def __init__(self, *, dim, depth, dim_head=64, heads=8, ff_mult=4, flash=True):
+        super().__init__()
+        assert dim_head == 64, "the sm_100a attention kernels are specialised for dim_head = 64"
+        self.dim, self.depth, self.heads, self.dim_head, self.ff_mult = dim, depth, heads, dim_head, ff_mult
+        self.layers = nn.ModuleList([nn.ModuleList([Attention(dim, dim_head, heads), Attention(dim, dim_head, heads, True),
+                                                    _ff_params(dim, ff_mult)]) for _ in range(depth)])
+        self.norm = LayerNorm(dim)
+
+
+# ------------------------------------------------------------------------------------------------ transformer
+class Transformer(nn.Module):
+    def __init__(self, *, num_tokens, dim, seq_len, dim_out=None, t5_name=DEFAULT_T5_NAME, self_cond=False,
+                 add_mask_id=False, precision=None, **kwargs):
+        super().__init__()
+        self.dim = dim
+        self.mask_id = num_tokens if add_mask_id else None
+        self.num_tokens, self.seq_len = num_tokens, seq_len
+        self.token_emb = nn.Embedding(num_tokens + int(add_mask_id), dim)
+        self.pos_emb = nn.Embedding(seq_len, dim)
+        self.transformer_blocks = TransformerBlocks(dim=dim, **kwargs)
+        self.norm = LayerNorm(dim)                       # present in checkpoints, never applied (reference defect B4)
+        self.dim_out = dim_out if dim_out is not None else num_tokens
+        self.to_logits = nn.Linear(dim, self.dim_out, bias=False)
+        self.encode_text = partial(t5_encode_text, name=t5_name)
+        text_dim = get_encoded_dim(t5_name)
+        self.text_embed_proj = nn.Linear(text_dim, dim, bias=False) if text_dim != dim else nn.Identity()
+        self.self_cond = self_cond
+        self.self_cond_to_init_embed = _ff_params(dim)
+        self.precision = precision or "bf16"
+        self._pack = None
+
+    # ----- packing ------------------------------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._pack = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._pack = None
+        return super().load_state_dict(*a, **k)
+
+    def _adt(self):
+        return torch.bfloat16 if self.precision == "bf16" else torch.float32
+
+    def _packed(self):
+        if self._pack is not None and self._pack["adt"] == self._adt():
+            return self._pack
+        dev = self.token_emb.weight.device
+        assert dev.type == "cuda", "Transformer runs on CUDA only (libmmg.so); there is no CPU path"
+        adt = self._adt()
+        tb = self.transformer_blocks
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        wa = lambda t: t.detach().to(dev, adt).contiguous()
+        P = dict(adt=adt, layers=[])
+
+        def ff_pack(ff):
+            F_ = ff[3].gamma.shape[0]
+            Fp = _round_up(F_, 64)
+            w1 = ff[1].weight.detach().to(dev, torch.float32)                  # (2F, dim): rows [0,F) -> gelu arm, [F,2F) -> gate
+            w1p = torch.zeros((2 * Fp, w1.shape[1]), device=dev)
+            xi = torch.arange(Fp, device=dev).view(-1, 32)
+            dst_x = (xi // 32 * 64 + xi % 32).reshape(-1)                       # unit u -> row 64*(u//32) + u%32 ; gate -> +32
+            valid = torch.arange(Fp, device=dev) < F_
+            w1p[dst_x[valid]] = w1[:F_]
+            w1p[dst_x[valid] + 32] = w1[F_:]
+            g3 = torch.zeros(Fp, device=dev); g3[:F_] = ff[3].gamma.detach().float()
+            w2 = torch.zeros((ff[4].weight.shape[0], Fp), device=dev); w2[:, :F_] = ff[4].weight.detach().float()
+            return dict(F=F_, Fp=Fp, g0=f32(ff[0].gamma), w1=w1p.to(adt).contiguous(), g3=g3.contiguous(), w2=w2.to(adt).contiguous())
+
+        for attn, cross, ff in tb.layers:
+            h = attn.heads
+            lay = dict(
+                sa=dict(g=f32(attn.norm.gamma), wqkv=wa(torch.cat((attn.to_q.weight, attn.to_kv.weight), 0)), wo=wa(attn.to_out.weight),
+                        qs=f32(attn.q_scale), ks=f32(attn.k_scale),
+                        nk=(torch.nn.functional.normalize(attn.null_kv[0].detach().float(), dim=-1) * attn.k_scale.detach().float()).to(dev, adt).contiguous(),
+                        nv=attn.null_kv[1].detach().to(dev, adt).contiguous()),
+                ca=dict(g=f32(cross.norm.gamma), wq=wa(cross.to_q.weight), wkv=wa(cross.to_kv.weight), wo=wa(cross.to_out.weight),
+                        qs=f32(cross.q_scale), ks=f32(cross.k_scale),
+                        nk=(torch.nn.functional.normalize(cross.null_kv[0].detach().float(), dim=-1) * cross.k_scale.detach().float()).to(dev, adt).contiguous(),
+                        nv=cross.null_kv[1].detach().to(dev, adt).contiguous(),
+                        # cross-attention output when every context key is masked: to_out(null_v)  (weight 1.0 on the null key)
+                        null_out=f32(cross.null_kv[1].detach().float().reshape(1, -1) @ cross.to_out.weight.detach().float().t()).reshape(-1)),
+                ff=ff_pack(ff))
+            P["layers"].append(lay)
+        P["gf"] = f32(tb.norm.gamma)
+        P["tok"], P["pos"] = f32(self.token_emb.weight), f32(self.pos_emb.weight)
+        P["wlog"] = wa(self.to_logits.weight)
+        P["wproj"] = wa(self.text_embed_proj.weight) if isinstance(self.text_embed_proj, nn.Linear) else None
+        P["sc"] = ff_pack(self.self_cond_to_init_embed) if self.self_cond else None
+        self._pack = P
+        return P
+
+    # ----- context (text / conditioning tokens): computed once per generate() ----------------------------------------
+    def _prepare_context(self, text_embeds, cond_ids, branches):
+        """Returns per-layer cross K/V buffers and the key mask for `branches` = list of drop flags (False = cond, True = text
+        dropped).  ref: muse_maskgit_pytorch.py:302-318."""
+        P = self._packed()
+        adt, dev = P["adt"], text_embeds.device
+        tb = self.transformer_blocks
+        b, m_text, _ = text_embeds.shape
+        te = text_embeds.to(torch.float32)
+        text_mask = (te != 0).any(dim=-1)                                           # muse_maskgit_pytorch.py:304
+        te_a = te.reshape(b * m_text, -1).to(adt).contiguous()
+        if P["wproj"] is not None:
+            ctx = torch.empty((b * m_text, self.dim), device=dev, dtype=adt)
+            ops.linear(te_a, P["wproj"], ctx)
+        else:
+            ctx = te_a
+        m = m_text
+        if cond_ids is not None:
+            cond_ids = cond_ids.reshape(b, -1).contiguous()
+            mc = cond_ids.shape[1]
+            cemb = torch.empty((b * mc, self.dim), device=dev, dtype=torch.float32)
+            ops.embed(cond_ids, P["tok"], None, cemb, n=mc, use_pos=False)             # token_emb only, no pos-emb (muse_maskgit_pytorch.py:316)
+            ctx = torch.cat((ctx.view(b, m_text, -1), cemb.to(adt).view(b, mc, -1)), dim=1).reshape(b * (m_text + mc), -1).contiguous()
+            m = m_text + mc
+        masks = []
+        for drop in branches:
+            tm = text_mask & (not drop)
+            if cond_ids is not None:
+                tm = torch.cat((tm, torch.ones((b, m - m_text), dtype=torch.bool, device=dev)), dim=1)
+            masks.append(tm)
+        key_mask = torch.cat(masks, 0).to(torch.uint8).contiguous()                # [len(branches)*b, m]
+        heads = tb.heads
+        tk_alloc = _round_up(m + 1, 8)
+        kvs = []
+        for lay in P["layers"]:
+            ca = lay["ca"]
+            k = torch.zeros((b * heads, tk_alloc, 64), device=dev, dtype=adt)
+            v = torch.zeros((b * heads, tk_alloc, 64), device=dev, dtype=adt)
+            epi = ops.qkv_epilogue(adt, heads, m, k=k, v=v, k_scale=ca["ks"], key_off=1, null_k=ca["nk"], null_v=ca["nv"])
+            ops.linear(ctx, ca["wkv"], None, epilogue=ops.EPI_QKV, epi=epi)
+            if len(branches) > 1:
+                k, v = k.repeat(len(branches), 1, 1), v.repeat(len(branches), 1, 1)
+            kvs.append((k, v))
+        return dict(kv=kvs, key_mask=key_mask, m=m, all_masked=[bool(d) and cond_ids is None for d in branches])
+
+    # ----- the block stack over R = nb*b*n rows -------------------------------------------------------------------------
+    def _workspace(self, nb, b, n, dev):
+        key = (nb, b, n, str(dev), self._adt())
+        ws = getattr(self, "_ws", None)
+        if ws is not None and ws["key"] == key:
+            return ws
+        P = self._packed()
+        adt, tb = P["adt"], self.transformer_blocks
+        heads, dim, inner = tb.heads, self.dim, tb.heads * 64
+        R = nb * b * n
+        Fp = max(l["ff"]["Fp"] for l in P["layers"])
+        tk_alloc = _round_up(n + 1, 8)
+        ws = dict(key=key,
+                  x=torch.empty((R, dim), device=dev, dtype=torch.float32),
+                  xn=torch.empty((R, dim), device=dev, dtype=adt),
+                  q=torch.empty((nb * b * heads, n, 64), device=dev, dtype=adt),
+                  k=torch.zeros((nb * b * heads, tk_alloc, 64), device=dev, dtype=adt),
+                  v=torch.zeros((nb * b * heads, tk_alloc, 64), device=dev, dtype=adt),
+                  ao=torch.empty((R, inner), device=dev, dtype=adt),
+                  h=torch.empty((R, Fp), device=dev, dtype=adt),
+                  hn=torch.empty((R, Fp), device=dev, dtype=adt))
+        self._ws = ws
+        return ws
+
+    def _run_blocks(self, ids, ctx, nb, self_cond_embed=None):
+        """ids (b, n) int64 -> residual stream x [nb*b*n, dim] fp32 after all blocks (before the final LayerNorm).
+        Branch j occupies rows [j*b*n, (j+1)*b*n).  ref: muse_maskgit_pytorch.py:322-330, 187-193"""
+        P = self._packed()
+        adt, tb = P["adt"], self.transformer_blocks
+        b, n = ids.shape
+        assert n <= self.seq_len
+        heads = tb.heads
+        dev = ids.device
+        ws = self._workspace(nb, b, n, dev)
+        x, xn, q, k, v, ao = ws["x"], ws["xn"], ws["q"], ws["k"], ws["v"], ws["ao"]
+        R, bn = nb * b * n, b * n
+        ops.embed(ids.contiguous(), P["tok"], P["pos"], x, n=n, copies=nb)
+        if self.self_cond:
+            sc = P["sc"]
+            e = torch.zeros((bn, self.dim), device=dev, dtype=torch.float32) if self_cond_embed is None else self_cond_embed.reshape(bn, -1).float().contiguous()
+            for j in range(nb):
+                self._ff(e, sc, x[j * bn:(j + 1) * bn], ws, bn)
+        for li, lay in enumerate(P["layers"]):
+            sa, ca, ff = lay["sa"], lay["ca"], lay["ff"]
+            # --- self attention (all branches) ---
+            ops.layernorm(x, sa["g"], xn)
+            epi = ops.qkv_epilogue(adt, heads, n, q=q, k=k, v=v, q_scale=sa["qs"], k_scale=sa["ks"], key_off=1,
+                                   null_k=sa["nk"], null_v=sa["nv"])
+            ops.linear(xn, sa["wqkv"], None, epilogue=ops.EPI_QKV, epi=epi)
+            ops.attention(q, k, v, ao, nb * b, heads, n + 1)
+            ops.linear(ao, sa["wo"], x, epilogue=ops.EPI_RESIDUAL, resid=x)
+            # --- cross attention ---
+            kc, vc = ctx["kv"][li]
+            live = [j for j in range(nb) if not ctx["all_masked"][j]]
+            pending_add = {j: ca["null_out"] for j in range(nb) if ctx["all_masked"][j]}
+            if live:
+                assert live == list(range(len(live))), "live branches must come first"
+                Rl = len(live) * bn
+                ops.layernorm(x[:Rl], ca["g"], xn[:Rl])
+                epi = ops.qkv_epilogue(adt, heads, n, q=q[:len(live) * b * heads], q_scale=ca["qs"])
+                ops.linear(xn[:Rl], ca["wq"], None, epilogue=ops.EPI_QKV, epi=epi)
+                ops.attention(q[:len(live) * b * heads], kc[:len(live) * b * heads], vc[:len(live) * b * heads], ao[:Rl], len(live) * b, heads,
+                              ctx["m"] + 1, key_mask=ctx["key_mask"][:len(live) * b])
+                ops.linear(ao[:Rl], ca["wo"], x[:Rl], epilogue=ops.EPI_RESIDUAL, resid=x[:Rl])
+            # --- feed forward (the constant null-branch cross-attention term is folded into this LayerNorm) ---
+            for j in range(nb):
+                xs = x[j * bn:(j + 1) * bn]
+                if j in pending_add:
+                    ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn], add=pending_add[j], x_out=xs)
+                else:
+                    ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn])
+            self._ff_tail(xn, ff, x, ws, R)
+        return x
+
+    def _ff_tail(self, xn, ff, x, ws, R):
+        h, hn = ws["h"][:R, :ff["Fp"]], ws["hn"][:R, :ff["Fp"]]
+        if ff["Fp"] != ws["h"].shape[1]:
+            h, hn = h.contiguous(), hn.contiguous()
+        ops.linear(xn[:R], ff["w1"], h, epilogue=ops.EPI_GEGLU)
+        ops.layernorm(h, ff["g3"], hn, width=ff["F"])
+        ops.linear(hn, ff["w2"], x[:R], epilogue=ops.EPI_RESIDUAL, resid=x[:R])
+
+    def _ff(self, inp, ff, x_acc, ws, R):
+        """x_acc += FeedForward(inp)   (self-conditioning embed, muse_maskgit_pytorch.py:325-328)"""
+        xn = ws["xn"][:R]
+        ops.layernorm(inp, ff["g0"], xn)
+        self._ff_tail(xn, ff, x_acc, ws, R)
+
+    # ----- public API ---------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, return_embed=False, return_logits=False, labels=None, ignore_index=0, self_cond_embed=None,
+                cond_drop_prob=0., conditioning_token_ids: Optional[torch.Tensor] = None, texts: Optional[List[str]] = None,
+                text_embeds: Optional[torch.Tensor] = None):
+        """ref: muse_maskgit_pytorch.py:279-348.  cond_drop_prob in {0, 1} is deterministic; other values draw one
+        Bernoulli per batch row like prob_mask_like."""
+        ids = x
+        b, n = ids.shape
+        assert (texts is not None) ^ (text_embeds is not None)
+        if texts is not None:
+            text_embeds = self.encode_text(texts)
+        text_embeds = text_embeds.to(ids.device)
+        if 0. < cond_drop_prob < 1.:
+            keep = torch.zeros((b, 1, 1), device=ids.device).uniform_(0, 1) < (1. - cond_drop_prob)
+            text_embeds = text_embeds * keep           # zero rows == masked keys (muse_maskgit_pytorch.py:304)
+        ctx = self._prepare_context(text_embeds, conditioning_token_ids, [cond_drop_prob == 1])
+        xres = self._run_blocks(ids, ctx, 1, self_cond_embed)
+        P = self._packed()
+        embed = torch.empty((b * n, self.dim), device=ids.device, dtype=torch.float32)
+        ops.layernorm(xres, P["gf"], embed)
+        logits = torch.empty((b * n, self.dim_out), device=ids.device, dtype=torch.float32)
+        ops.linear(embed.to(P["adt"]) if P["adt"] != torch.float32 else embed, P["wlog"], logits)
+        logits, embed = logits.view(b, n, -1), embed.view(b, n, -1)
+        if return_embed:
+            return logits, embed
+        if labels is None:
+            return logits
+        F = torch.nn.functional
+        if self.dim_out == 1:
+            loss = F.binary_cross_entropy_with_logits(logits[..., 0], labels)
+        else:
+            loss = F.cross_entropy(logits.transpose(1, 2), labels, ignore_index=ignore_index)
+        return (loss, logits) if return_logits else loss
+
+    @torch.no_grad()
+    def forward_with_cond_scale(self, *args, cond_scale=3., return_embed=False, **kwargs):
+        """ref: muse_maskgit_pytorch.py:240-259."""
+        if cond_scale == 1:
+            return self.forward(*args, return_embed=return_embed, cond_drop_prob=0., **kwargs)
+        logits, embed = self.forward(*args, return_embed=True, cond_drop_prob=0., **kwargs)
+        null_logits = self.forward(*args, cond_drop_prob=1., **kwargs)
+        scaled = null_logits + (logits - null_logits) * cond_scale
+        return (scaled, embed) if return_embed else scaled
+
+    def forward_with_neg_prompt(self, text_embed, neg_text_embed, cond_scale=3., return_embed=False, **kwargs):
+        raise NotImplementedError("negative prompting is broken in the reference (muse_maskgit_pytorch.py:261-277 references "
+                                  "undefined names); not part of the accelerated path")
+
+
+class MaskGitTransformer(Transformer):
+    def __init__(self, *args, **kwargs):
+        assert "add_mask_id" not in kwargs
+        super().__init__(*args, add_mask_id=True, **kwargs)
+
+
+class TokenCritic(Transformer):
+    def __init__(self, *args, **kwargs):
+        assert "dim_out" not in kwargs
+        super().__init__(*args, dim_out=1, **kwargs)
+
+
+def cosine_schedule(t):
+    return torch.cos(t * math.pi * 0.5)
+
+
+# ------------------------------------------------------------------------------------------------ MaskGit
+class MaskGit(nn.Module):
+    def __init__(self, image_size, transformer: MaskGitTransformer, noise_schedule: Callable = cosine_schedule,
+                 token_critic: Optional[TokenCritic] = None, self_token_critic=False, vae: Optional[VQGanVAE] = None,
+                 cond_vae: Optional[VQGanVAE] = None, cond_image_size=None, cond_drop_prob=0.5, self_cond_prob=0.9,
+                 no_mask_token_prob=0., critic_loss_weight=1.):
+        super().__init__()
+        assert isinstance(transformer, MaskGitTransformer), "transformer must be a MaskGitTransformer"
+        assert vae is None or isinstance(vae, VQGanVAE)
+        assert vae is not None, "a VQGanVAE is required (the reference dereferences it unconditionally, muse_maskgit_pytorch.py:462)"
+        self.vae = vae.copy_for_eval()
+        self.cond_vae = cond_vae.eval() if cond_vae is not None else self.vae
+        assert not (cond_vae is not None and cond_image_size is None), "cond_image_size must be specified if conditioning"
+        self.image_size, self.cond_image_size = image_size, cond_image_size
+        self.resize_image_for_cond_image = cond_image_size is not None
+        self.cond_drop_prob = cond_drop_prob
+        self.transformer = transformer
+        self.self_cond = transformer.self_cond
+        assert self.vae.codebook_size == self.cond_vae.codebook_size == transformer.num_tokens, \
+            "transformer num_tokens must be set to be equal to the vae codebook size"
+        self.mask_id = transformer.mask_id
+        self.noise_schedule = noise_schedule
+        assert not (self_token_critic and token_critic is not None)
+        self.token_critic = token_critic
+        if self_token_critic:
+            raise NotImplementedError("self token critic is not part of the accelerated path yet (SURVEY.md 8f #3)")
+        self.critic_loss_weight, self.self_cond_prob, self.no_mask_token_prob = critic_loss_weight, self_cond_prob, no_mask_token_prob
+        # sampler noise: None -> in-kernel Philox keyed on (seed, global row, vocab index); or a callable
+        # noise_fn(step, shape) -> U[0,1) tensor [b, n, V] (parity mode: the tensor the reference would draw)
+        self.sampler_seed = 0
+        self.sampler_noise_fn = None
+        self.row_offset = 0                 # global index of this shard's first sequence (multi-GPU batch sharding)
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        path = Path(path)
+        assert path.exists()
+        self.load_state_dict(torch.load(str(path)))
+
+    def mask_schedule(self, seq_len, timesteps):
+        """Data-independent, so evaluated on the host once (the reference syncs with .item() every step,
+        muse_maskgit_pytorch.py:558-559); same fp32 arithmetic."""
+        return [max(int((self.noise_schedule(t) * seq_len).item()), 1) for t in torch.linspace(0, 1, timesteps)]
+
+    @torch.no_grad()
+    def generate(self, texts: List[str], negative_texts: Optional[List[str]] = None, cond_images: Optional[torch.Tensor] = None,
+                 fmap_size=None, temperature=1., topk_filter_thres=0.9, can_remask_prev_masked=False,
+                 force_not_use_token_critic=False, timesteps=18, cond_scale=3, critic_noise_scale=1, return_ids=False):
+        """ref: muse_maskgit_pytorch.py:491-621.  Returns fp32 NCHW images (b, 3, H, W), unclamped."""
+        was_training = self.training
+        self.eval()
+        try:
+            return self._generate(texts, negative_texts, cond_images, fmap_size, temperature, topk_filter_thres,
+                                  can_remask_prev_masked, force_not_use_token_critic, timesteps, cond_scale, critic_noise_scale, return_ids)
+        finally:
+            self.train(was_training)
+
+    def _generate(self, texts, negative_texts, cond_images, fmap_size, temperature, topk_filter_thres, can_remask_prev_masked,
+                  force_not_use_token_critic, timesteps, cond_scale, critic_noise_scale, return_ids):
+        tr = self.transformer
+        if negative_texts is not None:
+            raise NotImplementedError("negative_texts raises TypeError in the reference (defect B2); not supported")
+        if self.token_critic is not None and not force_not_use_token_critic:
+            raise NotImplementedError("token-critic scoring is not part of the accelerated path yet (SURVEY.md 8f #3)")
+        if can_remask_prev_masked:
+            assert self.no_mask_token_prob > 0., "without training with some of the non-masked tokens forced to predict, not sure if the logits will be meaningful for these token"
+            raise NotImplementedError("can_remask_prev_masked=True is not implemented in the masked-rows-only sampler")
+        if self.self_cond:
+            raise NotImplementedError("self-conditioning feedback is not part of the accelerated path yet (SURVEY.md 8f #3)")
+        fmap_size = fmap_size if fmap_size is not None else self.vae.get_encoded_fmap_size(self.image_size)
+        device = next(self.parameters()).device
+        n = fmap_size ** 2
+        b = len(texts)
+        V = tr.num_tokens
+        text_embeds = tr.encode_text(texts).to(device)
+        cond_ids = None
+        if self.resize_image_for_cond_image:
+            assert cond_images is not None, "conditioning image must be passed in to generate for super res maskgit"
+            cond_ids = self.cond_vae.encode_ids(cond_images.to(device))
+        nb = 1 if cond_scale == 1 else 2
+        ctx = tr._prepare_context(text_embeds, cond_ids, [False, True][:nb])
+        P = tr._packed()
+        adt = P["adt"]
+        ids = torch.full((b, n), self.mask_id, dtype=torch.long, device=device)
+        scores = torch.zeros((b, n), dtype=torch.float32, device=device)
+        masked_pos = torch.empty((b, n), dtype=torch.int32, device=device)
+        k_keep = math.ceil((1 - topk_filter_thres) * V)                        # muse_maskgit_pytorch.py:414
+        sched = self.mask_schedule(n, timesteps)
+        e = torch.empty((b * n, tr.dim), device=device, dtype=adt)
+        logits = torch.empty((b * max(sched), V), device=device, dtype=torch.float32)
+        bn = b * n
+        for step, (num_masked, steps_until_x0) in enumerate(zip(sched, reversed(range(timesteps)))):
+            ops.remask(ids, scores, masked_pos, num_masked, self.mask_id)
+            x = tr._run_blocks(ids, ctx, nb)
+            R = b * num_masked
+            ops.final_embed(x[:bn], x[bn:2 * bn] if nb == 2 else None, P["gf"], masked_pos, e, b, n, num_masked, float(cond_scale))
+            lg = logits[:R]
+            ops.linear(e[:R], P["wlog"], lg)
+            temp = temperature * (steps_until_x0 / timesteps)                  # annealed, muse_maskgit_pytorch.py:578
+            u = None
+            if self.sampler_noise_fn is not None:
+                u = self.sampler_noise_fn(step, (b, n, V)).to(device=device, dtype=torch.float32).contiguous()
+            ops.logits_sample(lg, masked_pos, ids, scores, num_masked, k_keep, float(temp), u=u, seed=self.sampler_seed,
+                              step=step, row_offset=self.row_offset * n)
+        ids = ids.view(b, fmap_size, fmap_size)
+        images = self.vae.decode_from_ids(ids)
+        return (images, ids) if return_ids else images
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("MaskGit.forward is the training loss (muse_maskgit_pytorch.py:623-741); training is out of scope")
+
+
+# ------------------------------------------------------------------------------------------------ Muse
+class Muse(nn.Module):
+    """ref: muse_maskgit_pytorch.py:745-791 — base -> super-resolution cascade; the low-res images stay on the device."""
+    def __init__(self, base: MaskGit, superres: MaskGit):
+        super().__init__()
+        assert isinstance(base, MaskGit) and isinstance(superres, MaskGit)
+        self.base_maskgit = base.eval()
+        assert superres.resize_image_for_cond_image
+        self.superres_maskgit = superres.eval()
+
+    @torch.no_grad()
+    def forward(self, texts: List[str], cond_scale=3., temperature=1., timesteps=18, superres_timesteps=None,
+                return_lowres=False, return_pil_images=True):
+        lowres = self.base_maskgit.generate(texts=texts, cond_scale=cond_scale, temperature=temperature, timesteps=timesteps)
+        superres = self.superres_maskgit.generate(texts=texts, cond_scale=cond_scale, cond_images=lowres, temperature=temperature,
+                                                  timesteps=superres_timesteps if superres_timesteps is not None else timesteps)
+        if return_pil_images:
+            import torchvision.transforms as T
+            lowres = list(map(T.ToPILImage(), lowres))
+            superres = list(map(T.ToPILImage(), superres))
+        return (superres, lowres) if return_lowres else superres

@@ -1,0 +1,180 @@
+"""Thin tensor-level wrappers over the C-ABI (one Python function per mmg_* entry point).  PyTorch supplies device
+memory and the stream; every number is computed by libmmg.so."""
+import torch
+
+from . import _lib as L
+from ._lib import F32, BF16, EPI_STORE, EPI_RESIDUAL, EPI_GEGLU, EPI_GLU, EPI_QKV, EPI_CONVT, EPI_CONVT_RGB  # noqa: F401
+
+
+def _chk(t, name="tensor"):
+    assert t.is_cuda and t.is_contiguous(), f"{name} must be a contiguous CUDA tensor"
+    return t
+
+
+def _epi(out=None, ldo=0, bias=None, act=0, resid=None, ldr=0):
+    e = L.EpilogueArgs()
+    if out is not None:
+        e.out = out.data_ptr(); e.ldo = ldo; e.out_dtype = L.dt(out)
+    e.act = act
+    e.bias = L.ptr(bias)
+    if resid is not None:
+        e.resid = resid.data_ptr(); e.ldr = ldr
+    return e
+
+
+def linear(a, w, out, epilogue=EPI_STORE, bias=None, act=0, resid=None, M=None, N=None, epi=None):
+    """out = a @ w.T (+ epilogue).  a [M, K], w [N, K] same dtype (bf16 -> tcgen05, fp32 -> CUDA cores)."""
+    _chk(a, "a"); _chk(w, "w")
+    args = L.LinearArgs()
+    args.a = a.data_ptr(); args.w = w.data_ptr()
+    args.M = a.shape[0] if M is None else M
+    args.N = w.shape[0] if N is None else N
+    args.K = a.shape[1]; args.lda = a.stride(0); args.ldw = w.stride(0)
+    assert w.shape[1] == a.shape[1] and a.dtype == w.dtype
+    args.dtype = L.dt(a); args.epilogue = epilogue
+    if epi is None:
+        epi = _epi(out, out.stride(0), bias, act, resid, resid.stride(0) if resid is not None else 0)
+    args.epi = epi
+    L.call("mmg_linear", args)
+    return out
+
+
+def qkv_epilogue(dtype_t, heads, tokens, q=None, k=None, v=None, q_scale=None, k_scale=None, key_off=0, null_k=None, null_v=None):
+    """Epilogue block for MMG_EPI_QKV.  q [BH, q_rows, 64]; k, v [BH, kv_rows, 64]."""
+    e = L.EpilogueArgs()
+    e.out_dtype = L.F32 if dtype_t == torch.float32 else L.BF16
+    e.heads = heads; e.tokens = tokens; e.key_off = key_off
+    if q is not None:
+        e.q_out = q.data_ptr(); e.q_scale = q_scale.data_ptr(); e.q_rows = q.shape[1]; e.nq_heads = heads
+    if k is not None:
+        e.k_out = k.data_ptr(); e.k_scale = k_scale.data_ptr(); e.kv_rows = k.shape[1]; e.nk_heads = heads
+        e.v_out = v.data_ptr(); e.nv_heads = heads
+        e.null_k = L.ptr(null_k); e.null_v = L.ptr(null_v)
+    return e
+
+
+def conv2d(x, w, out, B, H, W, Cin, Cout, kind, epilogue=EPI_STORE, bias=None, act=0, resid=None):
+    """x [B,H,W,Cin] NHWC, w packed [Cout, taps*Cin]; out rows = output pixels."""
+    _chk(x); _chk(w)
+    a = L.Conv2dArgs()
+    a.x = x.data_ptr(); a.w = w.data_ptr(); a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.kind = kind
+    a.dtype = L.dt(x); a.epilogue = epilogue
+    ldo = out.shape[-1]
+    a.epi = _epi(out, ldo, bias, act, resid, resid.shape[-1] if resid is not None else 0)
+    L.call("mmg_conv2d", a)
+    return out
+
+
+def conv_transpose2d(x, w, out, B, H, W, Cin, Cout, bias=None, rgb_w=None, rgb_b=None):
+    """ConvTranspose2d(4,2,1) + LeakyReLU(0.1); with rgb_w: fused trailing 1x1 conv, out fp32 [B, ch, 2H, 2W]."""
+    _chk(x); _chk(w)
+    a = L.ConvTranspose2dArgs()
+    a.x = x.data_ptr(); a.w = w.data_ptr(); a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout
+    a.dtype = L.dt(x)
+    e = L.EpilogueArgs()
+    e.out = out.data_ptr(); e.bias = L.ptr(bias)
+    if rgb_w is not None:
+        a.epilogue = EPI_CONVT_RGB
+        e.out_dtype = L.F32; e.rgb_w = rgb_w.data_ptr(); e.rgb_b = rgb_b.data_ptr(); e.rgb_channels = rgb_w.shape[0]
+    else:
+        a.epilogue = EPI_CONVT
+        e.out_dtype = L.dt(out); e.ldo = Cout
+    a.epi = e
+    L.call("mmg_conv_transpose2d", a)
+    return out
+
+
+def conv_in(img, w, bias, out):
+    a = L.ConvInArgs()
+    B, Cc, H, W = img.shape
+    a.img = _chk(img).data_ptr(); a.w = _chk(w).data_ptr(); a.bias = L.ptr(bias); a.out = out.data_ptr()
+    a.B = B; a.C = Cc; a.H = H; a.W = W; a.Cout = w.shape[0]; a.out_dtype = L.dt(out)
+    L.call("mmg_conv_in", a)
+    return out
+
+
+def groupnorm_(x, gamma, beta, B, HW, Cch, groups=16, act=0):
+    a = L.GroupNormArgs()
+    a.x = _chk(x).data_ptr(); a.gamma = gamma.data_ptr(); a.beta = beta.data_ptr()
+    a.B = B; a.HW = HW; a.C = Cch; a.groups = groups; a.dtype = L.dt(x); a.act = act
+    L.call("mmg_groupnorm", a)
+    return x
+
+
+def layernorm(x, gamma, y, width=None, add=None, x_out=None, rows=None):
+    a = L.LayerNormArgs()
+    a.x = _chk(x).data_ptr(); a.x_dtype = L.dt(x); a.y = _chk(y).data_ptr(); a.y_dtype = L.dt(y)
+    a.gamma = gamma.data_ptr(); a.add = L.ptr(add); a.x_out = L.ptr(x_out)
+    a.rows = x.shape[0] if rows is None else rows
+    a.width = x.shape[1] if width is None else width
+    a.ldx = x.stride(0); a.ldy = y.stride(0)
+    L.call("mmg_layernorm", a)
+    return y
+
+
+def embed(ids, token_emb, pos_emb, x, n, copies=1, use_pos=True):
+    a = L.EmbedArgs()
+    a.ids = _chk(ids).data_ptr(); a.token_emb = token_emb.data_ptr(); a.pos_emb = L.ptr(pos_emb); a.x = x.data_ptr()
+    a.rows = ids.numel(); a.n = n; a.dim = token_emb.shape[1]; a.copies = copies; a.use_pos = int(use_pos)
+    L.call("mmg_embed", a)
+    return x
+
+
+def attention(q, k, v, out, B, heads, Tk, key_mask=None, kv_shared=False, scale=8.0):
+    """q [B*heads, Tq, 64]; k, v [(B or 1)*heads, Tk_alloc, 64]; out [B*Tq, heads*64]."""
+    a = L.AttentionArgs()
+    a.q = _chk(q).data_ptr(); a.k = _chk(k).data_ptr(); a.v = _chk(v).data_ptr(); a.out = out.data_ptr()
+    a.key_mask = L.ptr(key_mask)
+    a.B = B; a.heads = heads; a.Tq = q.shape[1]; a.Tk = Tk; a.Tk_alloc = k.shape[1]; a.dtype = L.dt(q)
+    a.ldo = out.stride(0); a.kv_batch_stride_zero = int(kv_shared); a.scale = scale
+    L.call("mmg_attention", a)
+    return out
+
+
+def remask(ids, scores, masked_pos, num_masked, mask_id):
+    a = L.RemaskArgs()
+    a.ids = ids.data_ptr(); a.scores = scores.data_ptr(); a.masked_pos = masked_pos.data_ptr()
+    a.B, a.n = ids.shape; a.num_masked = num_masked; a.mask_id = mask_id
+    L.call("mmg_remask", a)
+
+
+def final_embed(x_cond, x_null, gamma, masked_pos, e, B, n, num_masked, cond_scale):
+    a = L.FinalEmbedArgs()
+    a.x_cond = x_cond.data_ptr(); a.x_null = L.ptr(x_null); a.gamma = gamma.data_ptr(); a.masked_pos = masked_pos.data_ptr()
+    a.e = e.data_ptr(); a.e_dtype = L.dt(e); a.B = B; a.n = n; a.num_masked = num_masked; a.dim = gamma.shape[0]
+    a.cond_scale = cond_scale
+    L.call("mmg_final_embed", a)
+    return e
+
+
+def logits_sample(logits, masked_pos, ids, scores, num_masked, k, temperature, u=None, seed=0, step=0, row_offset=0):
+    a = L.LogitsSampleArgs()
+    a.logits = _chk(logits).data_ptr(); a.masked_pos = masked_pos.data_ptr(); a.ids = ids.data_ptr(); a.scores = scores.data_ptr()
+    a.u = L.ptr(u)
+    a.B, a.n = ids.shape; a.num_masked = num_masked; a.V = logits.shape[-1]; a.k = k; a.temperature = temperature
+    a.seed = seed; a.step = step; a.row_offset = row_offset
+    L.call("mmg_logits_sample", a)
+
+
+def vq_lfq_encode(x, w_in, b_in, ids, bits):
+    a = L.LfqEncodeArgs()
+    a.x = _chk(x).data_ptr(); a.dtype = L.dt(x); a.w_in = L.ptr(w_in); a.b_in = L.ptr(b_in); a.ids = ids.data_ptr()
+    a.T = x.shape[0]; a.D = x.shape[1]; a.bits = bits
+    L.call("mmg_vq_lfq_encode", a)
+    return ids
+
+
+def vq_l2_argmin(x, codebook, ids):
+    a = L.L2ArgminArgs()
+    a.x = _chk(x).data_ptr(); a.codebook = _chk(codebook).data_ptr(); a.ids = ids.data_ptr()
+    a.T = x.shape[0]; a.K = codebook.shape[0]; a.D = x.shape[1]
+    L.call("mmg_vq_l2_argmin", a)
+    return ids
+
+
+def vq_decode_codes(ids, w_out, b_out, out, bits):
+    a = L.DecodeCodesArgs()
+    a.ids = _chk(ids).data_ptr(); a.w_out = L.ptr(w_out); a.b_out = L.ptr(b_out); a.out = out.data_ptr()
+    a.dtype = L.dt(out); a.T = ids.numel(); a.D = out.shape[-1]; a.bits = bits
+    L.call("mmg_vq_decode_codes", a)
+    return out

@@ -1,0 +1,59 @@
+"""CPU: libmmg.so builds for sm_100a, loads without a GPU/driver, exports every symbol include/mmg.h declares, and the
+ctypes mirror of every argument block has the C struct's size.  No compute calls here."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_header_symbols():
+    from muse_maskgit_pytorch_b200 import build, _lib
+    build.build()
+    header = open(os.path.join(ROOT, "include", "mmg.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(mmg_[a-z0-9_]+)\s*\(", header, re.M))
+    assert {"mmg_linear", "mmg_attention", "mmg_logits_sample", "mmg_vq_lfq_encode", "mmg_vq_l2_argmin", "mmg_conv2d",
+            "mmg_conv_transpose2d", "mmg_remask", "mmg_version"} <= declared
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in mmg.h but not exported"
+    assert set(_lib.EXPORTS) | set(_lib.PLAIN_EXPORTS) == declared
+    assert _lib.lib().mmg_version() == 100          # also runs the struct-size self check
+
+
+def test_ops_fail_loudly_without_library(monkeypatch, tmp_path):
+    from muse_maskgit_pytorch_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "missing.so"))
+    try:
+        _lib.lib()
+    except _lib.MMGError as e:
+        assert "no fallback" in str(e)
+    else:
+        raise AssertionError("missing library must raise")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "muse_maskgit_pytorch_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), f"{fn} references the oracle"
+
+
+def test_state_dict_keys_match_reference_tables():
+    """Checkpoint-key contract: our parameter holders expose exactly the reference's keys/shapes
+    (oracle/shapes.py is asserted against the unmodified reference in tests/golden/make_golden.py)."""
+    import muse_maskgit_pytorch_b200 as M
+    from muse_maskgit_pytorch_b200 import t5
+    from oracle import shapes
+    t5.T5_CONFIGS["synth-96"] = {"d_model": 96}
+    tr = M.MaskGitTransformer(num_tokens=1024, dim=128, seq_len=16, depth=2, heads=2, t5_name="synth-96")
+    got = {k: tuple(v.shape) for k, v in tr.state_dict().items()}
+    assert got == {k: tuple(v) for k, v in shapes.transformer_shapes(1024, 128, 16, 2, heads=2, text_dim=96).items()}
+    vae = M.VQGanVAE(dim=64, codebook_size=512)
+    got = {k: tuple(v.shape) for k, v in vae.state_dict().items() if k != "quantizer.mask"}
+    assert got == {k: tuple(v) for k, v in shapes.vae_shapes(64, codebook_size=512).items()}
+    assert "quantizer.mask" in vae.state_dict()
+    critic = M.TokenCritic(num_tokens=1024, dim=128, seq_len=16, depth=1, heads=2, t5_name="synth-96")
+    assert critic.state_dict()["to_logits.weight"].shape == (1, 128) and critic.mask_id is None
