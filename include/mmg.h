@@ -205,6 +205,8 @@ typedef struct {
   int32_t B, n, num_masked, V, k;
   float temperature;
   uint64_t seed; uint64_t step; int64_t row_offset;  /* global row = row_offset + b*n + pos                        */
+  const uint64_t* seed_dev;  /* optional device word added to `seed` at run time (lets a captured CUDA graph be replayed
+                                with a fresh seed)                                                                   */
 } mmg_logits_sample_args;
 int mmg_logits_sample(const mmg_logits_sample_args* a, void* stream);
 

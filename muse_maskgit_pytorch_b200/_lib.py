@@ -76,7 +76,7 @@ class FinalEmbedArgs(C.Structure):
 class LogitsSampleArgs(C.Structure):
     _fields_ = [("logits", vp), ("masked_pos", vp), ("ids", vp), ("scores", vp), ("u", vp),
                 ("B", i32), ("n", i32), ("num_masked", i32), ("V", i32), ("k", i32), ("temperature", f32),
-                ("seed", u64), ("step", u64), ("row_offset", i64)]
+                ("seed", u64), ("step", u64), ("row_offset", i64), ("seed_dev", vp)]
 
 
 class LfqEncodeArgs(C.Structure):

@@ -55,7 +55,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   float* samp = reinterpret_cast<float*>(lidx + SMP_CAP);        // [SMP_SAMPLE]  (reused as perturbed values in phase C)
   __shared__ int s_count, s_n;
   __shared__ float s_redf[32]; __shared__ int s_redi[32]; __shared__ int s_redj[32];
-  __shared__ float s_max, s_sum, s_tlo;
+  __shared__ float s_max, s_sum;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = a.V, k = a.k;
@@ -220,6 +220,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
 
   // ---------------- phase C: perturbed argmax restricted to the exact top-k ----------------
   const int64_t grow = a.row_offset + (int64_t)b * a.n + pos;
+  const uint64_t seed = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
   constexpr int PER = (SMP_CAP + SMP_THREADS - 1) / SMP_THREADS;
   float pv[PER];
 #pragma unroll
@@ -230,7 +231,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
       const int v = lidx[s];
       float u;
       if (a.u) u = a.u[((int64_t)b * a.n + pos) * V + v];
-      else u = (float)(philox_first((uint32_t)v, (uint32_t)a.step, (uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32)) >> 8) * (1.0f / 16777216.0f);
+      else u = (float)(philox_first((uint32_t)v, (uint32_t)a.step, (uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), (uint32_t)seed, (uint32_t)(seed >> 32)) >> 8) * (1.0f / 16777216.0f);
       const float l1 = logf(fmaxf(u, 1e-20f));
       const float g = -logf(fmaxf(-l1, 1e-20f));
       p = __fdiv_rn(lval[s], tdiv) + g;

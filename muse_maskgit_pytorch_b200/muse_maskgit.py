@@ -374,8 +374,10 @@ class MaskGit(nn.Module):
         self.critic_loss_weight, self.self_cond_prob, self.no_mask_token_prob = critic_loss_weight, self_cond_prob, no_mask_token_prob
         # sampler noise: None -> in-kernel Philox keyed on (seed, global row, vocab index); or a callable
         # noise_fn(step, shape) -> U[0,1) tensor [b, n, V] (parity mode: the tensor the reference would draw)
-        self.sampler_seed = 0
+        self.sampler_seed = None            # None: one draw from torch's global generator per call (reproducible under manual_seed)
         self.sampler_noise_fn = None
+        self.use_cuda_graph = True
+        self._graphs = {}
         self.row_offset = 0                 # global index of this shard's first sequence (multi-GPU batch sharding)
 
     def save(self, path):
@@ -418,14 +420,58 @@ class MaskGit(nn.Module):
             raise NotImplementedError("self-conditioning feedback is not part of the accelerated path yet (SURVEY.md 8f #3)")
         fmap_size = fmap_size if fmap_size is not None else self.vae.get_encoded_fmap_size(self.image_size)
         device = next(self.parameters()).device
-        n = fmap_size ** 2
         b = len(texts)
-        V = tr.num_tokens
-        text_embeds = tr.encode_text(texts).to(device)
-        cond_ids = None
+        text_embeds = tr.encode_text(texts).to(device, non_blocking=True)
         if self.resize_image_for_cond_image:
             assert cond_images is not None, "conditioning image must be passed in to generate for super res maskgit"
-            cond_ids = self.cond_vae.encode_ids(cond_images.to(device))
+            cond_images = cond_images.to(device, torch.float32)
+        else:
+            cond_images = None
+        # per-call seed: explicit sampler_seed, else one draw from torch's global generator (reproducible under manual_seed)
+        seed = self.sampler_seed if self.sampler_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        if getattr(self, "_seed_dev", None) is None or self._seed_dev.device != device:
+            self._seed_dev = torch.zeros((1,), dtype=torch.int64, device=device)
+        self._seed_dev.fill_(seed)
+        body = partial(self._generate_body, fmap_size=fmap_size, temperature=temperature, topk_filter_thres=topk_filter_thres,
+                       timesteps=timesteps, cond_scale=cond_scale, b=b)
+        if not self.use_cuda_graph or self.sampler_noise_fn is not None:
+            images, ids = body(text_embeds, cond_images)
+            return (images, ids) if return_ids else images
+        # ---- whole-call CUDA graph: 18 decode steps + VAE decode replayed as one launch (no per-kernel host work) ----
+        key = (b, tuple(text_embeds.shape), text_embeds.dtype, None if cond_images is None else tuple(cond_images.shape), fmap_size,
+               float(temperature), float(topk_filter_thres), int(timesteps), float(cond_scale), int(self.row_offset), tr.precision, self.vae.precision)
+        entry = self._graphs.get(key)
+        if entry is not None and entry[5] != (id(tr._pack), id(self.vae._pack), id(self.cond_vae._pack)):
+            entry = None                                       # weights were re-packed (load_state_dict / .to()): re-capture
+        if entry is None:
+            te_s = text_embeds.clone()
+            ci_s = None if cond_images is None else cond_images.clone()
+            body(te_s, ci_s)                                   # eager warm-up: lazy packing, workspaces, function attributes
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out_images, out_ids = body(te_s, ci_s)
+            # the entry keeps alive everything the captured kernels point at (packed weights, workspaces)
+            entry = (graph, te_s, ci_s, out_images, out_ids, (id(tr._pack), id(self.vae._pack), id(self.cond_vae._pack)),
+                     (tr._pack, self.vae._pack, self.cond_vae._pack, tr._ws))
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = entry
+        graph, te_s, ci_s, out_images, out_ids = entry[:5]
+        te_s.copy_(text_embeds, non_blocking=True)
+        if ci_s is not None:
+            ci_s.copy_(cond_images, non_blocking=True)
+        graph.replay()
+        images, ids = out_images.clone(), out_ids.clone()
+        return (images, ids) if return_ids else images
+
+    def _generate_body(self, text_embeds, cond_images, *, fmap_size, temperature, topk_filter_thres, timesteps, cond_scale, b):
+        """The device-side work of generate(): no host synchronisation, no data-dependent host control flow."""
+        tr = self.transformer
+        device = text_embeds.device
+        n = fmap_size ** 2
+        V = tr.num_tokens
+        cond_ids = self.cond_vae.encode_ids(cond_images) if cond_images is not None else None
         nb = 1 if cond_scale == 1 else 2
         ctx = tr._prepare_context(text_embeds, cond_ids, [False, True][:nb])
         P = tr._packed()
@@ -449,11 +495,11 @@ class MaskGit(nn.Module):
             u = None
             if self.sampler_noise_fn is not None:
                 u = self.sampler_noise_fn(step, (b, n, V)).to(device=device, dtype=torch.float32).contiguous()
-            ops.logits_sample(lg, masked_pos, ids, scores, num_masked, k_keep, float(temp), u=u, seed=self.sampler_seed,
+            ops.logits_sample(lg, masked_pos, ids, scores, num_masked, k_keep, float(temp), u=u, seed=0, seed_dev=self._seed_dev,
                               step=step, row_offset=self.row_offset * n)
         ids = ids.view(b, fmap_size, fmap_size)
         images = self.vae.decode_from_ids(ids)
-        return (images, ids) if return_ids else images
+        return images, ids
 
     def forward(self, *args, **kwargs):
         raise NotImplementedError("MaskGit.forward is the training loss (muse_maskgit_pytorch.py:623-741); training is out of scope")

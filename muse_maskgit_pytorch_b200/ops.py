@@ -147,12 +147,12 @@ def final_embed(x_cond, x_null, gamma, masked_pos, e, B, n, num_masked, cond_sca
     return e
 
 
-def logits_sample(logits, masked_pos, ids, scores, num_masked, k, temperature, u=None, seed=0, step=0, row_offset=0):
+def logits_sample(logits, masked_pos, ids, scores, num_masked, k, temperature, u=None, seed=0, step=0, row_offset=0, seed_dev=None):
     a = L.LogitsSampleArgs()
     a.logits = _chk(logits).data_ptr(); a.masked_pos = masked_pos.data_ptr(); a.ids = ids.data_ptr(); a.scores = scores.data_ptr()
     a.u = L.ptr(u)
     a.B, a.n = ids.shape; a.num_masked = num_masked; a.V = logits.shape[-1]; a.k = k; a.temperature = temperature
-    a.seed = seed; a.step = step; a.row_offset = row_offset
+    a.seed = seed; a.step = step; a.row_offset = row_offset; a.seed_dev = L.ptr(seed_dev)
     L.call("mmg_logits_sample", a)
 
 

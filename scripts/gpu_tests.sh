@@ -7,20 +7,20 @@ nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > $OUT/gpu.
 run() { # name, timeout, args...
   local name=$1; local to=$2; shift 2
   echo "=== $name" | tee -a $OUT/summary.txt
-  timeout -k 10 $to python -m pytest "$@" -q -m gpu -x --no-header -p no:cacheprovider > $OUT/$name.log 2>&1
+  timeout -k 10 $to python -m pytest "$@" -q -rP -m gpu -x --no-header -p no:cacheprovider > $OUT/$name.log 2>&1
   echo "exit $?: $(tail -1 $OUT/$name.log)" | tee -a $OUT/summary.txt
 }
 runall() { # same but without -x
   local name=$1; local to=$2; shift 2
   echo "=== $name" | tee -a $OUT/summary.txt
-  timeout -k 10 $to python -m pytest "$@" -q -m gpu --no-header -p no:cacheprovider > $OUT/$name.log 2>&1
+  timeout -k 10 $to python -m pytest "$@" -q -rP -m gpu --no-header -p no:cacheprovider > $OUT/$name.log 2>&1
   echo "exit $?: $(tail -1 $OUT/$name.log)" | tee -a $OUT/summary.txt
 }
 : > $OUT/summary.txt
-runall k_fp32 600 tests/test_gpu_kernels.py -k "float32 or remask or sample or vq or embed or layernorm"
-runall k_bf16_gemm 300 tests/test_gpu_kernels.py -k "bfloat16 and linear"
-runall k_bf16_attn 300 tests/test_gpu_kernels.py -k "bfloat16 and attention"
-runall k_bf16_conv 300 tests/test_gpu_kernels.py -k "(bfloat16 and (conv or groupnorm)) or fused_rgb"
+runall k_fp32 600 tests/test_gpu_kernels.py -k "fp32 or remask or sample or vq or embed or layernorm"
+runall k_bf16_gemm 300 tests/test_gpu_kernels.py -k "bf16 and linear"
+runall k_bf16_attn 300 tests/test_gpu_kernels.py -k "bf16 and attention"
+runall k_bf16_conv 300 tests/test_gpu_kernels.py -k "(bf16 and (conv or groupnorm)) or fused_rgb"
 runall m_fp32 600 tests/test_gpu_models.py -k "fp32 or explicit"
 runall m_bf16 600 tests/test_gpu_models.py -k "bf16"
 cat $OUT/summary.txt

@@ -36,7 +36,7 @@ def close(a, b, atol, rtol=1e-3):
 
 # ------------------------------------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 512, 512), (300, 192, 128), (2048, 2816, 512), (512, 4096, 512), (4096, 512, 1408), (70, 64, 192)])
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 def test_linear_store(M, N, K, dtype):
     a, w = rnd(f"a{M}{K}", (M, K), dtype), rnd(f"w{N}{K}", (N, K), dtype, std=K ** -0.5)
     out = torch.empty((M, N), device="cuda", dtype=torch.float32)
@@ -45,7 +45,7 @@ def test_linear_store(M, N, K, dtype):
     assert ok, msg
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 def test_linear_bias_act_bf16_out(dtype):
     M, N, K = 384, 256, 256
     a, w, bias = rnd("a", (M, K), dtype), rnd("w", (N, K), dtype, std=K ** -0.5), rnd("b", (N,))
@@ -56,7 +56,7 @@ def test_linear_bias_act_bf16_out(dtype):
     assert ok, msg
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 def test_linear_residual_inplace(dtype):
     M, N, K = 512, 512, 512
     a, w, x = rnd("a", (M, K), dtype), rnd("w", (N, K), dtype, std=K ** -0.5), rnd("x", (M, N))
@@ -66,7 +66,7 @@ def test_linear_residual_inplace(dtype):
     assert ok, msg
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 def test_linear_geglu(dtype):
     """W rows interleaved [x(32) | gate(32)]: out[:, u] = gate_u * gelu(x_u)  (ref: muse_maskgit_pytorch.py:76-77)."""
     M, K, Fu = 256, 128, 96
@@ -82,7 +82,7 @@ def test_linear_geglu(dtype):
     assert ok, msg
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 def test_linear_qkv_epilogue(dtype):
     """fused head split + l2norm * scale + null key/value row  (ref: muse_maskgit_pytorch.py:141-153)."""
     b, n, heads, dim = 3, 20, 2, 128
@@ -94,7 +94,8 @@ def test_linear_qkv_epilogue(dtype):
     q = torch.zeros((b * heads, n, 64), device="cuda", dtype=dtype)
     k = torch.zeros((b * heads, n + 4, 64), device="cuda", dtype=dtype)
     v = torch.zeros_like(k)
-    e = ops().qkv_epilogue(dtype, heads, n, q=q, k=k, v=v, q_scale=dev(qs), k_scale=dev(ks), key_off=1, null_k=dev(nk, dtype), null_v=dev(nv, dtype))
+    qsd, ksd, nkd, nvd = dev(qs), dev(ks), dev(nk, dtype), dev(nv, dtype)      # keep alive: the epilogue block holds raw pointers
+    e = ops().qkv_epilogue(dtype, heads, n, q=q, k=k, v=v, q_scale=qsd, k_scale=ksd, key_off=1, null_k=nkd, null_v=nvd)
     ops().linear(dev(x, dtype), dev(w, dtype), None, epilogue=ops().EPI_QKV, epi=e)
     y = (x @ w.t()).view(b, n, 3, heads, 64).permute(2, 0, 3, 1, 4)          # (3, b, h, n, 64)
     qr = F.normalize(y[0], dim=-1) * qs
@@ -160,7 +161,7 @@ def attn_ref(q, k, v, mask, scale=8.0):
     return sim.softmax(-1) @ v
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 @pytest.mark.parametrize("Tq,Tk,masked", [(256, 257, False), (16, 17, False), (256, 33, True), (64, 81, True), (1024, 1025, False), (200, 290, True)])
 def test_attention(dtype, Tq, Tk, masked):
     b, heads = 2, 2
@@ -204,7 +205,7 @@ def test_remask():
     assert torch.equal(got, ref_set)
     assert torch.equal(idd.cpu()[~ref_set], ids[~ref_set])
     assert float(sd.max()) == -1e5 and float(sd.min()) == -1e5
-    pos = mp.cpu()[:, :nm].long()
+    pos = mp.cpu().view(-1)[:b * nm].view(b, nm).long()          # compact [B, num_masked] list
     assert torch.equal(pos, torch.sort(order, dim=-1).values)
 
 
@@ -286,7 +287,7 @@ def test_logits_sample_philox_is_shard_invariant():
 
 
 # ------------------------------------------------------------------------------------------------ VQ
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 def test_vq_lfq_encode_bit_exact(dtype):
     """dyadic inputs: every partial sum is exact in fp32, so ids must be bit-identical in any summation order."""
     T, D, bits = 300, 2048, 16
@@ -333,7 +334,7 @@ def pack_conv(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 @pytest.mark.parametrize("kind,B,H,W,Cin,Cout", [(1, 2, 16, 16, 64, 128), (1, 5, 2, 2, 128, 64), (2, 2, 32, 32, 64, 128), (2, 3, 4, 4, 64, 64),
                                                   (0, 2, 8, 8, 128, 128), (1, 1, 16, 16, 16, 32), (2, 1, 256, 256, 64, 64)])
 def test_conv2d(dtype, kind, B, H, W, Cin, Cout):
@@ -349,7 +350,7 @@ def test_conv2d(dtype, kind, B, H, W, Cin, Cout):
     assert ok, msg
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 def test_conv2d_glu_and_residual(dtype):
     B, H, W, C = 2, 16, 16, 64
     x = rnd("gx", (B, C, H, W), dtype)
@@ -382,7 +383,7 @@ def pack_convt(w):
     return torch.stack(packs).contiguous()
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 128, 64), (3, 2, 2, 64, 64), (1, 128, 128, 64, 64), (1, 8, 8, 32, 16)])
 def test_conv_transpose2d(dtype, B, H, W, Cin, Cout):
     x = rnd("tx", (B, Cin, H, W), dtype)
@@ -410,7 +411,7 @@ def test_conv_transpose2d_fused_rgb():
     assert ok, msg
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 def test_groupnorm_and_conv_in(dtype):
     B, HW, C = 2, 64, 128
     x = rnd("nx", (B, HW, C), dtype) * 2 + 0.3
