@@ -1,0 +1,50 @@
+"""Batch-sharded generation over the GPUs of one node: every sequence is independent through the whole
+of generate(), so rank r generates a contiguous slice of the batch with replicated weights and the decoded images are
+assembled with ONE all-gather at the end.  No collective runs inside the decode loop.  The sampler's Philox counters are
+keyed on the global sequence index (MaskGit.row_offset), so token ids do not depend on the number of ranks."""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(total, rank, world):
+    """Contiguous balanced split: the first (total % world) ranks get one extra item."""
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_batch(local, total, group=None):
+    """All-gather row-sharded tensors (shards from shard_bounds, possibly uneven) into the full batch on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    rank = dist.get_rank(group)
+    per = -(-total // world)
+    if total % world == 0:
+        out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    pieces = []
+    for r in range(world):
+        lo, hi = shard_bounds(total, r, world)
+        pieces.append(out[r * per:r * per + (hi - lo)])
+    return torch.cat(pieces, 0)
+
+
+def generate_sharded(maskgit, texts, text_embeds=None, cond_images=None, group=None, **generate_kwargs):
+    """maskgit.generate over this rank's slice of `texts` (+ optional pre-computed `text_embeds` [B, L, D] and
+    `cond_images` [B, ...], indexed by global row), then one all-gather.  Returns the full batch on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    total = len(texts)
+    lo, hi = shard_bounds(total, rank, world)
+    maskgit.row_offset = lo
+    if text_embeds is not None:
+        shard = text_embeds[lo:hi]
+        maskgit.transformer.encode_text = lambda t: shard
+    local = maskgit.generate(texts[lo:hi], cond_images=None if cond_images is None else cond_images[lo:hi], **generate_kwargs)
+    return gather_batch(local, total, group)
