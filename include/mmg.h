@@ -166,6 +166,9 @@ typedef struct {
   int64_t ldo;             /* out row stride (elements) = heads*64 normally                                      */
   int32_t kv_batch_stride_zero;  /* 1: k/v are shared by all batch entries (per head only)                        */
   float   scale;
+  float   logit_bound;     /* optional: a guaranteed upper bound on |q.k| (for l2-normalised q, k: max_i |q_scale_i k_scale_i|);
+                              > 0 lets the tensor-core kernel run a single-pass softmax against that fixed maximum. 0 = unknown. */
+  int32_t _pad;
 } mmg_attention_args;
 int mmg_attention(const mmg_attention_args* a, void* stream);
 

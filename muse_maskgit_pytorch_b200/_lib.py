@@ -60,7 +60,7 @@ class EmbedArgs(C.Structure):
 class AttentionArgs(C.Structure):
     _fields_ = [("q", vp), ("k", vp), ("v", vp), ("out", vp), ("key_mask", vp),
                 ("B", i32), ("heads", i32), ("Tq", i32), ("Tk", i32), ("Tk_alloc", i32), ("dtype", i32),
-                ("ldo", i64), ("kv_batch_stride_zero", i32), ("scale", f32)]
+                ("ldo", i64), ("kv_batch_stride_zero", i32), ("scale", f32), ("logit_bound", f32), ("_pad", i32)]
 
 
 class RemaskArgs(C.Structure):

@@ -90,6 +90,9 @@ int attention_tc_launch(const mmg_attention_args* a, cudaStream_t st) {
   attn_blocks(a->Tk, &p.nb, &p.KB);
   p.key_mask = a->key_mask; p.out = (bf16*)a->out; p.heads = a->heads; p.Tq = a->Tq; p.Tk = a->Tk; p.Tk_alloc = a->Tk_alloc;
   p.kv_shared = a->kv_batch_stride_zero; p.ldo = a->ldo; p.scale_log2e = a->scale * 1.4426950408889634f;
+  // single-pass softmax when the caller bounds |q.k| and exp2((s - bound) * scale * log2e) cannot underflow the fp32 range
+  p.smax = a->logit_bound;
+  p.single_pass = (a->logit_bound > 0.f && a->scale > 0.f && 2.f * a->logit_bound * p.scale_log2e < 100.f) ? 1 : 0;
   const uint64_t BH = (uint64_t)a->B * a->heads;
   const uint64_t kv_heads = a->kv_batch_stride_zero ? (uint64_t)a->heads : BH;
   {

@@ -24,6 +24,8 @@ struct alignas(64) AttnTcParams {
   int heads, Tq, Tk, Tk_alloc, nb, KB, kv_shared;
   int64_t ldo;
   float scale_log2e;
+  float smax;              // > 0: caller-guaranteed bound on |q.k| -> single-pass softmax with a fixed reference maximum
+  int single_pass;
 };
 
 template <uint32_t TMEM_COLS>
@@ -41,8 +43,8 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
   const int p_tiles = (KB + 63) / 64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + p_tiles * 16384);
   uint64_t* bar_q = bars + 0; uint64_t* bar_kv = bars + 1; uint64_t* bar_s = bars + 2;
-  uint64_t* bar_sdone = bars + 3; uint64_t* bar_p = bars + 4; uint64_t* bar_pv = bars + 5;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_sdone = bars + 3; uint64_t* bar_p = bars + 4; uint64_t* bar_pv = bars + 5; uint64_t* bar_k = bars + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / p.heads, h = bh % p.heads;
@@ -51,7 +53,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&p.tma_q); prefetch_tmap(&p.tma_k); prefetch_tmap(&p.tma_v);
-    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_sdone, 4); mbar_init(bar_p, 4); mbar_init(bar_pv, 1);
+    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_sdone, 4); mbar_init(bar_p, 4); mbar_init(bar_pv, 1); mbar_init(bar_k, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_ptr);
@@ -66,12 +68,51 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
     if (elect_one()) {
       const uint32_t idesc_s = idesc_bf16_f32(128, (uint32_t)KB, false, false);
       const uint32_t idesc_o = idesc_bf16_f32(128, 64, false, true);          // B (= V) is MN-major
+      const uint64_t qdesc = smem_desc_kmajor_sw128(smem_u32(sQ));
+      const uint64_t kdesc = smem_desc_kmajor_sw128(smem_u32(sK));
+      auto issue_s = [&]() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
+        umma_commit(bar_s);
+      };
+      auto issue_pv = [&](int blk) {
+        const int ksteps = KB / 16;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t pa = smem_u32(sP) + (ks >> 2) * 16384 + (ks & 3) * 32;
+          umma_f16(tO, smem_desc_kmajor_sw128(pa), smem_desc_mnmajor_sw128(smem_u32(sV) + ks * 2048, 1024), idesc_o, (blk | ks) ? 1u : 0u);
+        }
+        umma_commit(bar_pv);
+      };
+      if (p.single_pass) {
+        // K(blk+1) is fetched as soon as S(blk) has retired and V(blk) while the softmax of S(blk) runs: loads are off the
+        // critical path, which is  S-MMA -> softmax -> PV-MMA  per key block.
+        uint32_t ph_s = 0, ph_p = 0, ph_pv = 0, ph_v = 0, ph_k = 0;
+        const int krow0 = kvh * p.Tk_alloc;
+        mbar_expect_tx(bar_q, 16384 + kv_bytes);
+        tma_load_2d(sQ, &p.tma_q, bar_q, 0, bh * p.Tq + q0);
+        tma_load_2d(sK, &p.tma_k, bar_q, 0, krow0);
+        mbar_expect_tx(bar_kv, kv_bytes);
+        tma_load_2d(sV, &p.tma_v, bar_kv, 0, krow0);
+        mbar_wait(bar_q, 0);
+        tc_fence_after();
+        issue_s();
+        for (int blk = 0; blk < p.nb; ++blk) {
+          const bool more = blk + 1 < p.nb;
+          mbar_wait(bar_s, ph_s); ph_s ^= 1;                     // S(blk) retired: K smem reusable
+          if (more) { mbar_expect_tx(bar_k, kv_bytes); tma_load_2d(sK, &p.tma_k, bar_k, 0, krow0 + (blk + 1) * KB); }
+          mbar_wait(bar_p, ph_p); ph_p ^= 1;                     // P(blk) staged, S(blk) consumed
+          mbar_wait(bar_kv, ph_v); ph_v ^= 1;                    // V(blk) landed
+          tc_fence_after();
+          issue_pv(blk);
+          if (more) { mbar_wait(bar_k, ph_k); ph_k ^= 1; tc_fence_after(); issue_s(); }
+          mbar_wait(bar_pv, ph_pv); ph_pv ^= 1;                  // P / V smem reusable; after the last block O is final
+          if (more) { mbar_expect_tx(bar_kv, kv_bytes); tma_load_2d(sV, &p.tma_v, bar_kv, 0, krow0 + (blk + 1) * KB); }
+        }
+      } else {
       mbar_expect_tx(bar_q, 16384);
       tma_load_2d(sQ, &p.tma_q, bar_q, 0, bh * p.Tq + q0);
       mbar_wait(bar_q, 0);
       uint32_t ph_kv = 0, ph_sdone = 0, ph_p = 0, ph_pv = 0;
-      const uint64_t qdesc = smem_desc_kmajor_sw128(smem_u32(sQ));
-      const uint64_t kdesc = smem_desc_kmajor_sw128(smem_u32(sK));
       for (int pass = 0; pass < 2; ++pass) {
         for (int blk = 0; blk < p.nb; ++blk) {
           const int krow = kvh * p.Tk_alloc + blk * KB;
@@ -100,6 +141,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
           }
         }
       }
+      }
     }
     __syncwarp();
   } else {
@@ -111,8 +153,8 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
     uint32_t ph_s = 0, ph_pv = 0;
     float row_max = -FLT_MAX, row_sum = 0.f;
     float mneg = 0.f;
-    for (int pass = 0; pass < 2; ++pass) {
-      if (pass == 1) mneg = row_max * p.scale_log2e;
+    for (int pass = p.single_pass ? 1 : 0; pass < 2; ++pass) {
+      if (pass == 1) mneg = (p.single_pass ? p.smax : row_max) * p.scale_log2e;
       for (int blk = 0; blk < p.nb; ++blk) {
         mbar_wait(bar_s, ph_s); ph_s ^= 1;
         tc_fence_after();

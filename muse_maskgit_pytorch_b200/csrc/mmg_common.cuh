@@ -56,28 +56,57 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float leaky01(float x) { return x > 0.f ? x : 0.1f * x; }
 
-// load/store 64 consecutive elements of T from/to a 16B-aligned row chunk
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane
+__device__ __forceinline__ void st256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7) : "memory");
+}
+__device__ __forceinline__ void ld256(const void* p, uint32_t (&a)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]) : "l"(p));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) { __nv_bfloat162 t = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&t); }
+__device__ __forceinline__ bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+
+// load/store 64 consecutive elements of T from/to a 16B-aligned row chunk (256-bit accesses when 32B-aligned)
 template <typename T> struct Vec64;
 template <> struct Vec64<float> {
   static __device__ __forceinline__ void store(float* p, const float (&v)[64]) {
+    if (aligned32(p)) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      for (int i = 0; i < 8; ++i)
+        st256(p + 8 * i, __float_as_uint(v[8 * i]), __float_as_uint(v[8 * i + 1]), __float_as_uint(v[8 * i + 2]), __float_as_uint(v[8 * i + 3]),
+              __float_as_uint(v[8 * i + 4]), __float_as_uint(v[8 * i + 5]), __float_as_uint(v[8 * i + 6]), __float_as_uint(v[8 * i + 7]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
   }
   static __device__ __forceinline__ void load(const float* p, float (&v)[64]) {
+    if (aligned32(p)) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { float4 t = reinterpret_cast<const float4*>(p)[i]; v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
+      for (int i = 0; i < 8; ++i) { uint32_t a[8]; ld256(p + 8 * i, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * i + j] = __uint_as_float(a[j]); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { float4 t = reinterpret_cast<const float4*>(p)[i]; v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
+    }
   }
 };
 template <> struct Vec64<bf16> {
   static __device__ __forceinline__ void store(bf16* p, const float (&v)[64]) {
+    if (aligned32(p)) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      uint4 t;
-      __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), b = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-      __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), d = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-      t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
-      t.z = *reinterpret_cast<uint32_t*>(&c); t.w = *reinterpret_cast<uint32_t*>(&d);
-      reinterpret_cast<uint4*>(p)[i] = t;
+      for (int i = 0; i < 4; ++i)
+        st256(p + 16 * i, pack_bf16(v[16 * i], v[16 * i + 1]), pack_bf16(v[16 * i + 2], v[16 * i + 3]), pack_bf16(v[16 * i + 4], v[16 * i + 5]), pack_bf16(v[16 * i + 6], v[16 * i + 7]),
+              pack_bf16(v[16 * i + 8], v[16 * i + 9]), pack_bf16(v[16 * i + 10], v[16 * i + 11]), pack_bf16(v[16 * i + 12], v[16 * i + 13]), pack_bf16(v[16 * i + 14], v[16 * i + 15]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 t;
+        t.x = pack_bf16(v[8 * i], v[8 * i + 1]); t.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+        t.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]); t.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+        reinterpret_cast<uint4*>(p)[i] = t;
+      }
     }
   }
   static __device__ __forceinline__ void load(const bf16* p, float (&v)[64]) {
@@ -90,5 +119,17 @@ template <> struct Vec64<bf16> {
     }
   }
 };
+
+// erf to 1.5e-7 absolute (Abramowitz & Stegun 7.1.26) with MUFU rcp/ex2 — used by the bf16 tensor-core epilogues only
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f); p = fmaf(p, t, -0.284496736f); p = fmaf(p, t, 0.254829592f);
+  float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-ax * ax * 1.4426950408889634f));
+  const float r = fmaf(-p * t, e, 1.0f);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
 
 }  // namespace mmg

@@ -56,69 +56,89 @@ layernorm_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __re
   }
 }
 
-// Vectorised LayerNorm for 4-element-aligned rows: lane owns CH chunks of 4 consecutive columns (128-bit fp32 / 64-bit bf16
-// accesses, fully coalesced), statistics over the true width, columns in [width, ldy) written as 0.
-template <typename T> struct Ld4;
-template <> struct Ld4<float> {
-  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+// Vectorised LayerNorm: every lane moves 16 bytes per access (4 fp32 or 8 bf16 columns), CH chunks per lane cover the row,
+// statistics over the true width in fp32 (two-pass over registers, as F.layer_norm), columns in [width, ldy) written as 0.
+template <typename T> struct VecIO;
+template <> struct VecIO<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void ld(const float* p, float* v) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  static __device__ __forceinline__ void st(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 };
-template <> struct Ld4<bf16> {
-  static __device__ __forceinline__ void ld(const bf16* p, float (&v)[4]) {
-    const uint2 t = *reinterpret_cast<const uint2*>(p);
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+template <> struct VecIO<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void ld(const bf16* p, float* v) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
   }
-  static __device__ __forceinline__ void st(bf16* p, const float (&v)[4]) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-    uint2 t; t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p) = t;
+  static __device__ __forceinline__ void st(bf16* p, const float* v) {
+    uint4 t; uint32_t* u = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]); u[j] = *reinterpret_cast<uint32_t*>(&h); }
+    *reinterpret_cast<uint4*>(p) = t;
   }
 };
+// store N fp32 values as TY starting at p (N = 4 or 8)
+template <typename TY, int N> __device__ __forceinline__ void store_vec(TY* p, const float* v);
+template <> __device__ __forceinline__ void store_vec<float, 4>(float* p, const float* v) { VecIO<float>::st(p, v); }
+template <> __device__ __forceinline__ void store_vec<float, 8>(float* p, const float* v) { VecIO<float>::st(p, v); VecIO<float>::st(p + 4, v + 4); }
+template <> __device__ __forceinline__ void store_vec<bf16, 8>(bf16* p, const float* v) { VecIO<bf16>::st(p, v); }
+template <> __device__ __forceinline__ void store_vec<bf16, 4>(bf16* p, const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t; t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
 
 template <typename TX, typename TY, int CH>
 __global__ void __launch_bounds__(256)
 layernorm_vec_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ add,
                      float* __restrict__ x_out, int64_t rows, int width, int64_t ldx, int64_t ldy) {
+  constexpr int VN = VecIO<TX>::N;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const TX* xr = x + row * ldx;
-  float v[CH][4];
+  float v[CH][VN];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
-    const int c = (i * 32 + lane) * 4;
+    const int c = (i * 32 + lane) * VN;
     if (c < width) {
-      Ld4<TX>::ld(xr + c, v[i]);
-      if (add) { const float4 a = *reinterpret_cast<const float4*>(add + c);   // add is padded to a multiple of 4 by the caller contract (width % 4 == 0 when add != NULL)
-        v[i][0] += a.x; v[i][1] += a.y; v[i][2] += a.z; v[i][3] += a.w; }
+      VecIO<TX>::ld(xr + c, v[i]);
+      if (add) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { if (c + j >= width) v[i][j] = 0.f; sum += v[i][j]; }
+        for (int j = 0; j < VN; j += 4) { const float4 a = *reinterpret_cast<const float4*>(add + c + j); v[i][j] += a.x; v[i][j + 1] += a.y; v[i][j + 2] += a.z; v[i][j + 3] += a.w; }
+      }
+#pragma unroll
+      for (int j = 0; j < VN; ++j) { if (c + j >= width) v[i][j] = 0.f; sum += v[i][j]; }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[i][j] = 0.f;
+      for (int j = 0; j < VN; ++j) v[i][j] = 0.f;
     }
   }
   const float mean = warp_sum(sum) / (float)width;
   float sq = 0.f;
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
-    const int c = (i * 32 + lane) * 4;
+    const int c = (i * 32 + lane) * VN;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) if (c + j < width) { const float d = v[i][j] - mean; sq += d * d; }
+    for (int j = 0; j < VN; ++j) if (c + j < width) { const float d = v[i][j] - mean; sq += d * d; }
   }
   const float rstd = rsqrtf(warp_sum(sq) / (float)width + 1e-5f);
   TY* yr = y + row * ldy;
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
-    const int c = (i * 32 + lane) * 4;
+    const int c = (i * 32 + lane) * VN;
     if (c < ldy) {
-      float o[4];
+      float o[VN];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = (c + j < width) ? (v[i][j] - mean) * rstd * __ldg(gamma + c + j) : 0.f;
-      Ld4<TY>::st(yr + c, o);
-      if (x_out && c < width) *reinterpret_cast<float4*>(x_out + row * ldx + c) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+      for (int j = 0; j < VN; ++j) o[j] = (c + j < width) ? (v[i][j] - mean) * rstd * __ldg(gamma + c + j) : 0.f;
+      store_vec<TY, VN>(yr + c, o);
+      if (x_out && c < width) {
+#pragma unroll
+        for (int j = 0; j < VN; j += 4) *reinterpret_cast<float4*>(x_out + row * ldx + c + j) = make_float4(v[i][j], v[i][j + 1], v[i][j + 2], v[i][j + 3]);
+      }
     }
   }
 }
@@ -288,11 +308,14 @@ extern "C" int mmg_layernorm(const mmg_layernorm_args* a, void* stream) {
   if (a->rows == 0) return MMG_OK;
   const unsigned grid = (unsigned)((a->rows + 7) / 8);
   const int w = (int)a->width;
-  const bool vec = (a->ldx % 4 == 0) && (a->ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a->y) & 15) == 0) &&
-                   (!a->add || (w % 4 == 0 && (reinterpret_cast<uintptr_t>(a->add) & 15) == 0)) && (!a->x_out || w % 4 == 0) && a->ldy <= LN_MAXV * 128 &&
-                   ((w + 3) / 4 * 4 <= a->ldx);
+  const int vn = a->x_dtype == MMG_BF16 ? 8 : 4;                      // columns per 16-byte access of the input
+  const int64_t span = a->ldy > w ? a->ldy : w;
+  const bool vec = (a->ldx % vn == 0) && (a->ldy % vn == 0) && ((reinterpret_cast<uintptr_t>(a->x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a->y) & 15) == 0) &&
+                   (!a->add || (w % vn == 0 && (reinterpret_cast<uintptr_t>(a->add) & 15) == 0)) && (!a->x_out || w % vn == 0) &&
+                   ((w + vn - 1) / vn * vn <= a->ldx) && span <= 16 * 32 * vn;
 #define LNV(TX, TY, CH) layernorm_vec_kernel<TX, TY, CH><<<grid, 256, 0, st>>>((const TX*)a->x, (TY*)a->y, a->gamma, a->add, a->x_out, a->rows, w, a->ldx, a->ldy)
-#define LNV_DISPATCH(TX, TY) do { const int64_t span = a->ldy > w ? a->ldy : w; if (span <= 512) LNV(TX, TY, 4); else if (span <= 1024) LNV(TX, TY, 8); else LNV(TX, TY, 16); } while (0)
+#define LNV_DISPATCH(TX, TY) do { const int64_t per = 32 * vn; const int ch = (int)((span + per - 1) / per); \
+    if (ch <= 4) LNV(TX, TY, 4); else if (ch <= 6) LNV(TX, TY, 6); else if (ch <= 8) LNV(TX, TY, 8); else LNV(TX, TY, 16); } while (0)
 #define LN_LAUNCH(TX, TY) layernorm_kernel<TX, TY><<<grid, 256, 0, st>>>((const TX*)a->x, (TY*)a->y, a->gamma, a->add, a->x_out, a->rows, w, a->ldx, a->ldy)
   if (a->x_dtype == MMG_F32 && a->y_dtype == MMG_F32) { if (vec) LNV_DISPATCH(float, float); else LN_LAUNCH(float, float); }
   else if (a->x_dtype == MMG_F32 && a->y_dtype == MMG_BF16) { if (vec) LNV_DISPATCH(float, bf16); else LN_LAUNCH(float, bf16); }

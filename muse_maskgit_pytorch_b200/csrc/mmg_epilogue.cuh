@@ -8,6 +8,7 @@ namespace mmg {
 struct Epilogue {
   mmg_epilogue_args p;
   int kind;
+  int fast;                 // 1: tensor-core (bf16) path — MUFU-based erf/sigmoid are accurate far beyond bf16 output precision
   int64_t M, N;
   float rgb_acc[4];
 
@@ -88,7 +89,7 @@ struct Epilogue {
         float o[32];
         if (kind == MMG_EPI_GEGLU) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = v[32 + i] * gelu_erf(v[i]);
+          for (int i = 0; i < 32; ++i) o[i] = v[32 + i] * (fast ? gelu_fast(v[i]) : gelu_erf(v[i]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -131,7 +132,7 @@ struct Epilogue {
           for (int i = 0; i < 64; ++i) ss += v[i] * v[i];
           const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] = v[i] * inv * __ldg(sc + i);
+          for (int i = 0; i < 64; ++i) v[i] = v[i] * inv * sc[i];
         }
         if (bf) Vec64<bf16>::store(reinterpret_cast<bf16*>(dst) + off, v);
         else    Vec64<float>::store(reinterpret_cast<float*>(dst) + off, v);

@@ -159,7 +159,7 @@ extern "C" int mmg_linear(const mmg_linear_args* a, void* stream) {
   MMG_CHECK_ARG(a && a->a && a->w, "mmg_linear: NULL operand");
   MMG_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "mmg_linear: bad shape M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K);
   int rc = validate_epilogue(a->epilogue, a->epi, a->N); if (rc) return rc;
-  Epilogue epi; epi.p = a->epi; epi.kind = a->epilogue; epi.M = a->M; epi.N = a->N;
+  Epilogue epi; epi.p = a->epi; epi.kind = a->epilogue; epi.fast = 0; epi.M = a->M; epi.N = a->N;
   const bool tc_ok = a->dtype == MMG_BF16 && (a->K % 64 == 0) && (a->N % 64 == 0) && (a->lda % 8 == 0) && (a->ldw % 8 == 0) &&
                      aligned16(a->a) && aligned16(a->w) && (a->epi.ldo % 8 == 0 || a->epilogue == MMG_EPI_QKV || a->epilogue == MMG_EPI_CONVT_RGB);
   if (!tc_ok) {
@@ -169,7 +169,7 @@ extern "C" int mmg_linear(const mmg_linear_args* a, void* stream) {
   TcGemmParams p{};
   p.M = a->M; p.N = a->N; p.num_kb = (int)(a->K / TC_BK); p.mode = 0;
   p.num_m_tiles = (int)((a->M + TC_BM - 1) / TC_BM);
-  p.epi = epi;
+  p.epi = epi; p.epi.fast = 1;
   uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M}; uint64_t str[1] = {(uint64_t)a->lda * 2}; uint32_t box[2] = {TC_BK, TC_BM};
   rc = make_tmap_bf16(&p.tma_a[0], a->a, 2, dims, str, box); if (rc) return rc;
   const int bn = pick_bn(p.num_m_tiles, a->N, a->epilogue);
@@ -185,7 +185,7 @@ extern "C" int mmg_conv2d(const mmg_conv2d_args* a, void* stream) {
   ConvGeom g; conv_geom(a->kind, a->B, a->H, a->W, a->Cin, &g);
   const int64_t M = (int64_t)a->B * g.Ho * g.Wo, N = a->Cout, K = (int64_t)g.ntaps * a->Cin;
   int rc = validate_epilogue(a->epilogue, a->epi, N); if (rc) return rc;
-  Epilogue epi; epi.p = a->epi; epi.kind = a->epilogue; epi.M = M; epi.N = N;
+  Epilogue epi; epi.p = a->epi; epi.kind = a->epilogue; epi.fast = 0; epi.M = M; epi.N = N;
   TcGemmParams p{};
   const bool tc_ok = a->dtype == MMG_BF16 && a->kind != 3 && (a->Cin % 64 == 0) && (N % 64 == 0) && aligned16(a->x) && aligned16(a->w) &&
                      (a->epi.ldo % 8 == 0) && tile_geometry(g.Ho, g.Wo, &p) == 0;
@@ -193,7 +193,7 @@ extern "C" int mmg_conv2d(const mmg_conv2d_args* a, void* stream) {
   p.M = M; p.N = N; p.mode = 1; p.cchunks = a->Cin / 64; p.ntaps = g.ntaps; p.num_kb = p.ntaps * p.cchunks;
   p.Ho = g.Ho; p.Wo = g.Wo; p.B = a->B;
   p.num_m_tiles = p.tiles_x * p.tiles_y * ((a->B + p.TB - 1) / p.TB);
-  p.epi = epi;
+  p.epi = epi; p.epi.fast = 1;
   const uint64_t C = a->Cin, W = a->W, H = a->H;
   uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
   if (a->kind != 2) {
@@ -231,7 +231,7 @@ extern "C" int mmg_conv_transpose2d(const mmg_conv_transpose2d_args* a, void* st
                      tile_geometry(a->H, a->W, &p) == 0;
   const size_t esz = a->dtype == MMG_BF16 ? 2 : 4;
   for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px) {
-    Epilogue epi; epi.p = a->epi; epi.kind = a->epilogue; epi.M = M; epi.N = N;
+    Epilogue epi; epi.p = a->epi; epi.kind = a->epilogue; epi.fast = 0; epi.M = M; epi.N = N;
     epi.p.H = a->H; epi.p.W = a->W; epi.p.py = py; epi.p.px = px;
     const uint8_t* wp = reinterpret_cast<const uint8_t*>(a->w) + (size_t)(py * 2 + px) * N * K * esz;
     if (!tc_ok) {
@@ -244,7 +244,7 @@ extern "C" int mmg_conv_transpose2d(const mmg_conv_transpose2d_args* a, void* st
     q.M = M; q.N = N; q.mode = 1; q.cchunks = a->Cin / 64; q.ntaps = 4; q.num_kb = 4 * q.cchunks;
     q.Ho = a->H; q.Wo = a->W; q.B = a->B;
     q.num_m_tiles = q.tiles_x * q.tiles_y * ((a->B + q.TB - 1) / q.TB);
-    q.epi = epi;
+    q.epi = epi; q.epi.fast = 1;
     const uint64_t C = a->Cin, W = a->W, H = a->H;
     uint64_t dims[4] = {C, W, H, (uint64_t)a->B}; uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
     uint32_t box[4] = {64, (uint32_t)q.TW, (uint32_t)q.TH, (uint32_t)q.TB};

@@ -2,7 +2,8 @@
 //
 //   warp 0      : TMA producer  (one elected lane) — A tile 128x64 and W tile BNx64 per k-block, SWIZZLE_128B
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane) — 4 x tcgen05.mma (K=16) per k-block, M=128, N=BN
-//   warps 2..5  : epilogue — tcgen05.ld (32 lanes x 32 cols) -> registers -> fused Epilogue -> global
+//   warps 2..9  : epilogue — tcgen05.ld (32 lanes x 32 cols) -> registers -> fused Epilogue -> global; two warps share a TMEM
+//                 lane quarter and take alternate 64-column chunks
 //   persistent grid (<= #SM CTAs), static tile schedule, STAGES-deep smem ring, 2 accumulator stages in TMEM so the
 //   epilogue of tile i overlaps the main loop of tile i+1.
 //
@@ -18,7 +19,8 @@ namespace mmg {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_MAX_TAPS = 16;
 
 struct alignas(64) TcGemmParams {
@@ -60,12 +62,17 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  __shared__ float s_scale[128];               // QKV epilogue: q_scale | k_scale staged once per CTA
+  if (p.epi.kind == MMG_EPI_QKV && threadIdx.x < 128) {
+    const float* src = threadIdx.x < 64 ? p.epi.p.q_scale : p.epi.p.k_scale;
+    s_scale[threadIdx.x] = src ? src[threadIdx.x & 63] : 1.f;
+  }
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tma_b);
     prefetch_tmap(&p.tma_a[0]);
     for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
@@ -130,9 +137,12 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     }
   } else {
     // ===================== epilogue warps =====================
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access (warp id % 4)
+    const int half = (warp - 2) >> 2;             // 0: even 64-column chunks, 1: odd chunks
     const int r_in_tile = quarter * 32 + lane;
     Epilogue epi = p.epi;
+    if (epi.kind == MMG_EPI_QKV) { epi.p.q_scale = s_scale; epi.p.k_scale = s_scale + 64; }
+    const bool whole_row = (epi.kind == MMG_EPI_CONVT_RGB);      // needs every chunk of a row in one thread
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % p.num_m_tiles, n_blk = tile / p.num_m_tiles;
@@ -149,9 +159,11 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      if (valid) epi.begin_row(row);
+      const bool mine = !whole_row || half == 0;
+      if (valid && mine) epi.begin_row(row);
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
+      for (int c = (whole_row ? 0 : half); c < BN / 64; c += (whole_row ? 1 : 2)) {
+        if (!mine) break;
         float v[64];
         tmem_ld_32x32b_x32(t_row + c * 64, v);
         tmem_ld_32x32b_x32(t_row + c * 64 + 32, v + 32);
@@ -159,7 +171,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         const int col0 = n_blk * BN + c * 64;
         if (valid && col0 < p.N) epi.apply(row, col0, v, 64);
       }
-      if (valid) epi.end_row(row);
+      if (valid && mine) epi.end_row(row);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);

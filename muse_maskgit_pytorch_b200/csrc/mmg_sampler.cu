@@ -44,16 +44,31 @@ __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint3
   return c0;
 }
 
-struct ArgBest { float val; int idx; };          // idx: list slot (for exclusion) ; tie -> lowest vocabulary index
 __device__ __forceinline__ bool better(float v, int vi, float w, int wi) { return v > w || (v == w && vi < wi); }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float key_to_float(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
+// block-wide sum of two packed counters (each < 2^15), one __syncthreads pair; result broadcast to every thread
+__device__ __forceinline__ void block_sum2(int a, int b, int* red, int warp, int lane, int& oa, int& ob) {
+  a = __reduce_add_sync(0xffffffffu, a); b = __reduce_add_sync(0xffffffffu, b);
+  __syncthreads();
+  if (lane == 0) { red[warp] = a; red[32 + warp] = b; }
+  __syncthreads();
+  oa = 0; ob = 0;
+#pragma unroll
+  for (int w = 0; w < SMP_THREADS / 32; ++w) { oa += red[w]; ob += red[32 + w]; }
+}
+
+// EXACT = injected-noise parity mode: IEEE division and accurate logf so the perturbed values match the reference's
+// fp32 arithmetic as closely as a GPU can; otherwise (in-kernel Philox) fast MUFU-based logs and a reciprocal multiply.
+template <bool EXACT>
 __global__ void __launch_bounds__(SMP_THREADS)
 logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   extern __shared__ uint8_t smraw[];
-  float* lval = reinterpret_cast<float*>(smraw);                 // [SMP_CAP]
-  int* lidx = reinterpret_cast<int*>(lval + SMP_CAP);            // [SMP_CAP]
-  float* samp = reinterpret_cast<float*>(lidx + SMP_CAP);        // [SMP_SAMPLE]  (reused as perturbed values in phase C)
+  float* lval = reinterpret_cast<float*>(smraw);                 // [SMP_CAP] candidate logits
+  int* lidx = reinterpret_cast<int*>(lval + SMP_CAP);            // [SMP_CAP] candidate vocabulary indices
   __shared__ int s_count, s_n;
+  __shared__ int s_red[64];
   __shared__ float s_redf[32]; __shared__ int s_redi[32]; __shared__ int s_redj[32];
   __shared__ float s_max, s_sum;
 
@@ -64,83 +79,76 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   const int pos = a.masked_pos[r];
   const float* row = a.logits + r * (int64_t)V;
 
-  // ---------------- phase A: sample -> provisional threshold ----------------
+  // ---------------- phase A: sample (registers) -> provisional threshold ----------------
   const int ns = V < SMP_SAMPLE ? V : SMP_SAMPLE;
+  constexpr int SPT = SMP_SAMPLE / SMP_THREADS;                  // sample keys per thread
+  uint32_t sk[SPT];
   {
-    // 32-element lines spread evenly over the row
-    const int nlines = ns / 32, vlines = V / 32;
-    for (int i = tid; i < ns; i += SMP_THREADS) {
-      int src;
-      if (ns == V) src = i; else { const int ln = i >> 5; src = (int)(((int64_t)ln * vlines) / nlines) * 32 + (i & 31); }
-      samp[i] = row[src];
+    const int nlines = ns / 32, vlines = V / 32;                 // 128-byte lines spread evenly over the row
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      const int i = tid + j * SMP_THREADS;
+      uint32_t key = 0;                                          // key 0 sorts below every real value
+      if (i < ns) {
+        const int src = (ns == V) ? i : (int)(((int64_t)(i >> 5) * vlines) / nlines) * 32 + (i & 31);
+        key = fkey(row[src]);
+      }
+      sk[j] = key;
     }
   }
   if (tid == 0) s_count = 0;
-  __syncthreads();
   float tlo;
   {
-    // rank of the provisional threshold inside the sample
     int rs;
     if (ns == V) rs = k;
     else { const float pf = (float)k / (float)V; const float mu = pf * ns; rs = (int)(mu + 4.5f * sqrtf(mu * (1.f - pf)) + 2.f); }
     if (rs > ns) rs = ns;
-    // bitwise radix descent on the sample keys: largest key t with count(key >= t) >= rs  == rs-th largest sample
+    // radix descent, two key bits per round: largest t with count(key >= t) >= rs (sampled rows: 20 bits suffice for a lower bound)
     uint32_t prefix = 0;
-    for (int bit = 31; bit >= (ns == V ? 0 : 12); --bit) {   // sampled rows: 20 key bits are enough for a lower bound
-      const uint32_t cand = prefix | (1u << bit);
-      int c = 0;
-      for (int i = tid; i < ns; i += SMP_THREADS) c += (fkey(samp[i]) >= cand);
-      c = __reduce_add_sync(0xffffffffu, c);
-      __syncthreads();
-      if (lane == 0) s_redi[warp] = c;
-      __syncthreads();
-      int tot = 0;
+    const int last = (ns == V) ? 0 : 12;
+    for (int bit = 30; bit >= last; bit -= 2) {
+      const uint32_t c1 = prefix | (1u << bit), c2 = prefix | (2u << bit), c3 = prefix | (3u << bit);
+      int n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
-      for (int w = 0; w < SMP_THREADS / 32; ++w) tot += s_redi[w];
-      if (tot >= rs) prefix = cand;
+      for (int j = 0; j < SPT; ++j) { n1 += (sk[j] >= c1); n2 += (sk[j] >= c2); n3 += (sk[j] >= c3); }
+      int t12, t3;
+      block_sum2(n1 | (n2 << 16), n3, s_red, warp, lane, t12, t3);
+      const int t1 = t12 & 0xffff, t2 = t12 >> 16;
+      if (t3 >= rs) prefix = c3; else if (t2 >= rs) prefix = c2; else if (t1 >= rs) prefix = c1;
     }
-    const uint32_t u = (prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix;
-    tlo = __uint_as_float(u);
+    tlo = key_to_float(prefix);
+    if (prefix == 0) tlo = -FLT_MAX;
   }
+  const bool degenerate = (tlo == -FLT_MAX);                         // no usable threshold: every element is a candidate (-> exact rebuild)
 
-  // ---------------- phase B: one streaming pass ----------------
-  float m_t = -FLT_MAX, s_t = 0.f;
-  auto visit = [&](float x) {
-    if (x > m_t) { s_t = s_t * expf(m_t - x) + 1.f; m_t = x; } else { s_t += expf(x - m_t); }
-  };
-  auto append = [&](const bool* f, const float* xs, int base) {   // warp-aggregated append of this lane's flagged candidates
-    const int c = (int)f[0] + (int)f[1] + (int)f[2] + (int)f[3];
-    int incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    const int tot = __shfl_sync(0xffffffffu, incl, 31);
-    if (tot == 0) return;
-    int start = 0;
-    if (lane == 0) start = atomicAdd(&s_count, tot);
-    start = __shfl_sync(0xffffffffu, start, 0) + incl - c;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) if (f[j]) { if (start < SMP_CAP) { lval[start] = xs[j]; lidx[start] = base + j; } ++start; }
-  };
+  // ---------------- phase B: one streaming pass over the row ----------------
+  constexpr float LOG2E = 1.4426950408889634f;
+  float m_t = -FLT_MAX, s_t = 0.f;                                 // running max and sum of 2^((x - m) * log2e)
   if ((V & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
     const float4* r4 = reinterpret_cast<const float4*>(row);
     const int n4 = V >> 2;
-    for (int i0 = 0; i0 < n4; i0 += SMP_THREADS) {
-      const int i = i0 + tid;
-      float xs[4] = {0.f, 0.f, 0.f, 0.f}; bool f[4] = {false, false, false, false};
-      if (i < n4) {
-        const float4 q = ld_stream4(r4 + i);
-        xs[0] = q.x; xs[1] = q.y; xs[2] = q.z; xs[3] = q.w;
+    constexpr int UNR = 4;                                          // 4 independent 128-bit loads in flight per thread
+    for (int i0 = 0; i0 < n4; i0 += SMP_THREADS * UNR) {
+      float xs[UNR * 4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { visit(xs[j]); f[j] = (xs[j] >= tlo); }
+      for (int u = 0; u < UNR; ++u) {
+        const int i = i0 + u * SMP_THREADS + tid;
+        float4 q = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+        if (i < n4) q = ld_stream4(r4 + i);
+        xs[4 * u] = q.x; xs[4 * u + 1] = q.y; xs[4 * u + 2] = q.z; xs[4 * u + 3] = q.w;
       }
-      append(f, xs, i * 4);
-    }
-  } else {
-    for (int i0 = 0; i0 < V; i0 += SMP_THREADS) {
-      const int i = i0 + tid;
-      float xs[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX}; int c = 0;
-      if (i < V) { xs[0] = ld_stream(row + i); visit(xs[0]); c = (xs[0] >= tlo); }
-      // lanes hold one element each: positions base+0 only
+      float lm = xs[0];
+#pragma unroll
+      for (int j = 1; j < UNR * 4; ++j) lm = fmaxf(lm, xs[j]);
+      if (lm > m_t) { s_t *= ex2_approx((m_t - lm) * LOG2E); m_t = lm; }
+      const float mb = m_t * LOG2E;
+      int c = 0;
+#pragma unroll
+      for (int j = 0; j < UNR * 4; ++j) {                            // padding lanes hold -FLT_MAX: contribute 2^-inf = 0
+        s_t += ex2_approx(fmaf(xs[j], LOG2E, -mb));
+        c += ((xs[j] >= tlo) | degenerate) & (i0 + (j >> 2) * SMP_THREADS + tid < n4);
+      }
+      // warp-aggregated append (one shared-memory atomic per warp per 16 elements)
       int incl = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -149,21 +157,53 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
         int start = 0;
         if (lane == 0) start = atomicAdd(&s_count, tot);
         start = __shfl_sync(0xffffffffu, start, 0) + incl - c;
-        if (c && start < SMP_CAP) { lval[start] = xs[0]; lidx[start] = i; }
+        if (c) {
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * SMP_THREADS + tid;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x = xs[4 * u + j];
+              if (i < n4 && ((x >= tlo) | degenerate)) { if (start < SMP_CAP) { lval[start] = x; lidx[start] = i * 4 + j; } ++start; }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    for (int i0 = 0; i0 < V; i0 += SMP_THREADS) {
+      const int i = i0 + tid;
+      float x = -FLT_MAX; int c = 0;
+      if (i < V) {
+        x = ld_stream(row + i);
+        if (x > m_t) { s_t *= ex2_approx((m_t - x) * LOG2E); m_t = x; }
+        s_t += ex2_approx((x - m_t) * LOG2E);
+        c = (x >= tlo) | degenerate;
+      }
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const int tot = __shfl_sync(0xffffffffu, incl, 31);
+      if (tot) {
+        int start = 0;
+        if (lane == 0) start = atomicAdd(&s_count, tot);
+        start = __shfl_sync(0xffffffffu, start, 0) + incl - c;
+        if (c && start < SMP_CAP) { lval[start] = x; lidx[start] = i; }
       }
     }
   }
   // block softmax statistics
   {
     float m = warp_max(m_t);
+    __syncthreads();
     if (lane == 0) s_redf[warp] = m;
     __syncthreads();
     float M = s_redf[lane % (SMP_THREADS / 32)];
     M = warp_max(M);
-    float s = s_t * expf(m_t - M);
-    s = warp_sum(s);
+    float sm = s_t * ex2_approx((m_t - M) * LOG2E);
+    sm = warp_sum(sm);
     __syncthreads();
-    if (lane == 0) s_redf[warp] = s;
+    if (lane == 0) s_redf[warp] = sm;
     __syncthreads();
     if (tid == 0) { float t = 0.f; for (int w = 0; w < SMP_THREADS / 32; ++w) t += s_redf[w]; s_sum = t; s_max = M; s_n = s_count; }
     __syncthreads();
@@ -172,22 +212,17 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
 
   // ---------------- rare: exact rebuild when the sample threshold missed ----------------
   if (n < k || n > SMP_CAP) {
-    // k-th largest key of the row by bitwise descent (row is L2 resident now)
-    uint32_t prefix = 0;
+    uint32_t prefix = 0;                       // k-th largest key of the row by bitwise descent (row is L2 resident now)
     for (int bit = 31; bit >= 0; --bit) {
       const uint32_t cand = prefix | (1u << bit);
       int c = 0;
       for (int i = tid; i < V; i += SMP_THREADS) c += (fkey(row[i]) >= cand);
-      c = __reduce_add_sync(0xffffffffu, c);
-      __syncthreads();
-      if (lane == 0) s_redi[warp] = c;
-      __syncthreads();
-      int tot = 0;
-#pragma unroll
-      for (int w = 0; w < SMP_THREADS / 32; ++w) tot += s_redi[w];
+      int tot, dummy;
+      block_sum2(c, 0, s_red, warp, lane, tot, dummy);
       if (tot >= k) prefix = cand;
     }
     // list = all keys > prefix (fewer than k of them), then ties (== prefix) in index order until k entries
+    __syncthreads();
     if (tid == 0) s_count = 0;
     __syncthreads();
     for (int i0 = 0; i0 < V; i0 += SMP_THREADS) {
@@ -221,6 +256,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   // ---------------- phase C: perturbed argmax restricted to the exact top-k ----------------
   const int64_t grow = a.row_offset + (int64_t)b * a.n + pos;
   const uint64_t seed = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
+  const float inv_t = 1.0f / tdiv;
   constexpr int PER = (SMP_CAP + SMP_THREADS - 1) / SMP_THREADS;
   float pv[PER];
 #pragma unroll
@@ -229,18 +265,21 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
     float p = -FLT_MAX;
     if (s < n) {
       const int v = lidx[s];
-      float u;
-      if (a.u) u = a.u[((int64_t)b * a.n + pos) * V + v];
-      else u = (float)(philox_first((uint32_t)v, (uint32_t)a.step, (uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), (uint32_t)seed, (uint32_t)(seed >> 32)) >> 8) * (1.0f / 16777216.0f);
-      const float l1 = logf(fmaxf(u, 1e-20f));
-      const float g = -logf(fmaxf(-l1, 1e-20f));
-      p = __fdiv_rn(lval[s], tdiv) + g;
+      if (EXACT) {
+        const float u = a.u[((int64_t)b * a.n + pos) * V + v];
+        const float l1 = logf(fmaxf(u, 1e-20f));
+        p = __fdiv_rn(lval[s], tdiv) - logf(fmaxf(-l1, 1e-20f));
+      } else {
+        const float u = (float)(philox_first((uint32_t)v, (uint32_t)a.step, (uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), (uint32_t)seed, (uint32_t)(seed >> 32)) >> 8) * (1.0f / 16777216.0f);
+        const float l1 = __logf(fmaxf(u, 1e-20f));
+        p = fmaf(lval[s], inv_t, -__logf(fmaxf(-l1, 1e-20f)));
+      }
     }
     pv[j] = p;
   }
   int win_v = -1; float win_x = 0.f;
   for (int iter = 0; iter < n; ++iter) {
-    // block argmax of perturbed value (ties -> lowest vocabulary index)
+    // block argmax of the perturbed value (ties -> lowest vocabulary index)
     float bv = -FLT_MAX; int bi = 0x7fffffff, bs = -1;
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
@@ -261,23 +300,16 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
       const float ov = s_redf[w]; const int oi = s_redi[w], os = s_redj[w];
       if (os >= 0 && (bs < 0 || better(ov, oi, bv, bi))) { bv = ov; bi = oi; bs = os; }
     }
-    // exact rank of the candidate inside the row (list covers everything >= its value)
+    // exact rank of the candidate inside the row (the list covers everything >= its value)
     const float cx = lval[bs];
     int c = 0;
     for (int s = tid; s < n; s += SMP_THREADS) { const float x = lval[s]; c += (x > cx) || (x == cx && lidx[s] < bi); }
-    c = __reduce_add_sync(0xffffffffu, c);
-    __syncthreads();
-    if (lane == 0) s_redi[warp] = c;
-    __syncthreads();
-    int rank = 0;
-#pragma unroll
-    for (int w = 0; w < SMP_THREADS / 32; ++w) rank += s_redi[w];
+    int rank, dummy;
+    block_sum2(c, 0, s_red, warp, lane, rank, dummy);
     if (rank < k) { win_v = bi; win_x = cx; break; }
-    // not in the top-k: exclude and retry
     // not in the kept set: drop its perturbed value (its logit stays in the list for later rank computations)
 #pragma unroll
     for (int j = 0; j < PER; ++j) if (tid + j * SMP_THREADS == bs) pv[j] = -FLT_MAX;
-    __syncthreads();
   }
   if (tid == 0) {
     if (win_v < 0) { win_v = 0; win_x = row[0]; }                 // degenerate rows (all -inf / NaN)
@@ -335,11 +367,13 @@ extern "C" int mmg_logits_sample(const mmg_logits_sample_args* a, void* stream) 
   MMG_CHECK_ARG(a->k >= 1 && a->k <= a->V && a->k <= SMP_CAP, "mmg_logits_sample: k=%d out of range (<= %d)", a->k, SMP_CAP);
   const int64_t R = (int64_t)a->B * a->num_masked;
   if (R == 0) return MMG_OK;
-  static const size_t smem = (size_t)SMP_CAP * 8 + (size_t)SMP_SAMPLE * 4;
-  static cudaError_t attr = cudaFuncSetAttribute(logits_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (attr != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(logits_sample): %s", cudaGetErrorString(attr));
+  static const size_t smem = (size_t)SMP_CAP * 8;
+  static cudaError_t attr0 = cudaFuncSetAttribute(logits_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static cudaError_t attr1 = cudaFuncSetAttribute(logits_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (attr0 != cudaSuccess || attr1 != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(logits_sample): %s", cudaGetErrorString(attr0 != cudaSuccess ? attr0 : attr1));
   float t = a->temperature; if (t < 1e-10f) t = 1e-10f;      // max(temperature, 1e-10): muse_maskgit_pytorch.py:411
-  logits_sample_kernel<<<(unsigned)R, SMP_THREADS, smem, st>>>(*a, t);
+  if (a->u) logits_sample_kernel<true><<<(unsigned)R, SMP_THREADS, smem, st>>>(*a, t);
+  else logits_sample_kernel<false><<<(unsigned)R, SMP_THREADS, smem, st>>>(*a, t);
   MMG_LAUNCHED();
   return MMG_OK;
 }

@@ -128,10 +128,12 @@ class Transformer(nn.Module):
             lay = dict(
                 sa=dict(g=f32(attn.norm.gamma), wqkv=wa(torch.cat((attn.to_q.weight, attn.to_kv.weight), 0)), wo=wa(attn.to_out.weight),
                         qs=f32(attn.q_scale), ks=f32(attn.k_scale),
+                        bound=1.02 * float((attn.q_scale.detach().abs() * attn.k_scale.detach().abs()).max()),   # |q.k| <= max_i|qs_i ks_i| for unit q, k (+ bf16 slack)
                         nk=(torch.nn.functional.normalize(attn.null_kv[0].detach().float(), dim=-1) * attn.k_scale.detach().float()).to(dev, adt).contiguous(),
                         nv=attn.null_kv[1].detach().to(dev, adt).contiguous()),
                 ca=dict(g=f32(cross.norm.gamma), wq=wa(cross.to_q.weight), wkv=wa(cross.to_kv.weight), wo=wa(cross.to_out.weight),
                         qs=f32(cross.q_scale), ks=f32(cross.k_scale),
+                        bound=1.02 * float((cross.q_scale.detach().abs() * cross.k_scale.detach().abs()).max()),
                         nk=(torch.nn.functional.normalize(cross.null_kv[0].detach().float(), dim=-1) * cross.k_scale.detach().float()).to(dev, adt).contiguous(),
                         nv=cross.null_kv[1].detach().to(dev, adt).contiguous(),
                         # cross-attention output when every context key is masked: to_out(null_v)  (weight 1.0 on the null key)
@@ -240,7 +242,7 @@ class Transformer(nn.Module):
             epi = ops.qkv_epilogue(adt, heads, n, q=q, k=k, v=v, q_scale=sa["qs"], k_scale=sa["ks"], key_off=1,
                                    null_k=sa["nk"], null_v=sa["nv"])
             ops.linear(xn, sa["wqkv"], None, epilogue=ops.EPI_QKV, epi=epi)
-            ops.attention(q, k, v, ao, nb * b, heads, n + 1)
+            ops.attention(q, k, v, ao, nb * b, heads, n + 1, logit_bound=sa["bound"])
             ops.linear(ao, sa["wo"], x, epilogue=ops.EPI_RESIDUAL, resid=x)
             # --- cross attention ---
             kc, vc = ctx["kv"][li]
@@ -253,7 +255,7 @@ class Transformer(nn.Module):
                 epi = ops.qkv_epilogue(adt, heads, n, q=q[:len(live) * b * heads], q_scale=ca["qs"])
                 ops.linear(xn[:Rl], ca["wq"], None, epilogue=ops.EPI_QKV, epi=epi)
                 ops.attention(q[:len(live) * b * heads], kc[:len(live) * b * heads], vc[:len(live) * b * heads], ao[:Rl], len(live) * b, heads,
-                              ctx["m"] + 1, key_mask=ctx["key_mask"][:len(live) * b])
+                              ctx["m"] + 1, key_mask=ctx["key_mask"][:len(live) * b], logit_bound=ca["bound"])
                 ops.linear(ao[:Rl], ca["wo"], x[:Rl], epilogue=ops.EPI_RESIDUAL, resid=x[:Rl])
             # --- feed forward (the constant null-branch cross-attention term is folded into this LayerNorm) ---
             for j in range(nb):

@@ -120,13 +120,13 @@ def embed(ids, token_emb, pos_emb, x, n, copies=1, use_pos=True):
     return x
 
 
-def attention(q, k, v, out, B, heads, Tk, key_mask=None, kv_shared=False, scale=8.0):
+def attention(q, k, v, out, B, heads, Tk, key_mask=None, kv_shared=False, scale=8.0, logit_bound=0.0):
     """q [B*heads, Tq, 64]; k, v [(B or 1)*heads, Tk_alloc, 64]; out [B*Tq, heads*64]."""
     a = L.AttentionArgs()
     a.q = _chk(q).data_ptr(); a.k = _chk(k).data_ptr(); a.v = _chk(v).data_ptr(); a.out = out.data_ptr()
     a.key_mask = L.ptr(key_mask)
     a.B = B; a.heads = heads; a.Tq = q.shape[1]; a.Tk = Tk; a.Tk_alloc = k.shape[1]; a.dtype = L.dt(q)
-    a.ldo = out.stride(0); a.kv_batch_stride_zero = int(kv_shared); a.scale = scale
+    a.ldo = out.stride(0); a.kv_batch_stride_zero = int(kv_shared); a.scale = scale; a.logit_bound = logit_bound
     L.call("mmg_attention", a)
     return out
 

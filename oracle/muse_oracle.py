@@ -164,7 +164,7 @@ def remask(ids, scores, num_masked, mask_id):
 
 
 def generate_ids(sd, cfg, text_embeds, seq_len, mask_id, noise_fn, cond_ids=None, timesteps=18,
-                 cond_scale=3.0, temperature=1.0, topk_thres=0.9, trace=None):
+                 cond_scale=3.0, temperature=1.0, topk_thres=0.9, trace=None, max_steps=None):
     """ref: muse_maskgit_pytorch.py:507-613 (token loop of MaskGit.generate; self_cond / critic off).
 
     noise_fn(step, shape) -> U[0,1) fp32 tensor, standing in for `zeros_like(t).uniform_(0, 1)`
@@ -174,6 +174,8 @@ def generate_ids(sd, cfg, text_embeds, seq_len, mask_id, noise_fn, cond_ids=None
     scores = torch.zeros((b, seq_len), dtype=torch.float32)
     sched = mask_schedule(seq_len, timesteps)
     for step, (num_masked, steps_until_x0) in enumerate(zip(sched, reversed(range(timesteps)))):
+        if max_steps is not None and step >= max_steps:      # bounded CPU-baseline sample (bench.py): stop early
+            break
         ids = remask(ids, scores, num_masked, mask_id)
         logits, _ = forward_with_cond_scale(sd, cfg, ids, text_embeds, cond_ids, cond_scale)
         temp = temperature * (steps_until_x0 / timesteps)

@@ -162,8 +162,9 @@ def attn_ref(q, k, v, mask, scale=8.0):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+@pytest.mark.parametrize("bound", [0.0, 1.02], ids=["twopass", "singlepass"])
 @pytest.mark.parametrize("Tq,Tk,masked", [(256, 257, False), (16, 17, False), (256, 33, True), (64, 81, True), (1024, 1025, False), (200, 290, True)])
-def test_attention(dtype, Tq, Tk, masked):
+def test_attention(dtype, Tq, Tk, masked, bound):
     b, heads = 2, 2
     if Tq == 1024:
         b = 1
@@ -181,7 +182,7 @@ def test_attention(dtype, Tq, Tk, masked):
     vd = torch.zeros_like(kd); vd[:, :Tk] = dev(v.reshape(b * heads, Tk, 64), dtype)
     out = torch.empty((b * Tq, heads * 64), device="cuda", dtype=dtype)
     ops().attention(dev(q.reshape(b * heads, Tq, 64), dtype).contiguous(), kd, vd, out, b, heads, Tk,
-                    key_mask=None if mask is None else dev(mask.to(torch.uint8)))
+                    key_mask=None if mask is None else dev(mask.to(torch.uint8)), logit_bound=bound)
     ref = attn_ref(q, k, v, mask).transpose(1, 2).reshape(b * Tq, heads * 64)
     ok, msg = close(out, ref, 2e-2 if dtype == torch.bfloat16 else 2e-5, 2e-2 if dtype == torch.bfloat16 else 1e-4)
     assert ok, msg
