@@ -56,6 +56,9 @@ enum mmg_epilogue {
   MMG_EPI_QKV        = 4, /* N = (nq+nk+nv)*64 head-columns: l2norm(q)*q_scale, l2norm(k)*k_scale, v -> per-head layouts */
   MMG_EPI_CONVT      = 5, /* conv-transpose parity scatter: out pixel (2y+py, 2x+px) = leaky(acc + bias)             */
   MMG_EPI_CONVT_RGB  = 6, /* CONVT followed by the fused final 1x1 conv (C -> channels<=4), fp32 NCHW output          */
+  MMG_EPI_LNFOLD_RESIDUAL = 7, /* LayerNorm folded through the product: with W' = W*gamma, cvec[c] = sum_k W'[c,k] (passed as
+                                  `bias`) and per-row (sum, sumsq) of the un-normalised A row in `row_stats`:
+                                  out[r,c] = resid[r,c] + rstd_r * (acc - mean_r * cvec[c])   == resid + LN(a_r) W^T           */
 };
 
 typedef struct {
@@ -74,6 +77,9 @@ typedef struct {
   int32_t      heads, tokens, q_rows, kv_rows, key_off, nq_heads, nk_heads, nv_heads;
   /* CONVT(_RGB): input geometry of the GEMM rows (b, y, x) and the output parity                                  */
   int32_t      H, W, py, px;
+  float*       row_stats;  /* [M, 2] fp32 (sum, sum of squares). GEGLU: the epilogue atomically ACCUMULATES its fp32 outputs;
+                              LNFOLD_RESIDUAL: read (statistics over ln_width columns, eps 1e-5)                       */
+  int32_t      ln_width; int32_t _pad0;
   const float* rgb_w;      /* CONVT_RGB: [channels, N] fp32 1x1 weights, rgb_b [channels]                          */
   const float* rgb_b;
   int32_t      rgb_channels;
@@ -142,6 +148,7 @@ typedef struct {
   const float* gamma;      /* [width]                                                                            */
   const float* add;        /* [width] or NULL                                                                    */
   float*       x_out;      /* fp32 [rows, ldx] or NULL                                                           */
+  float*       zero_stats; /* optional [rows, 2]: reset to 0 (row statistics accumulated by a later GEGLU epilogue)     */
   int64_t rows, width, ldx, ldy;
 } mmg_layernorm_args;
 int mmg_layernorm(const mmg_layernorm_args* a, void* stream);

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmmg.so")
 
 F32, BF16 = 0, 1
-EPI_STORE, EPI_RESIDUAL, EPI_GEGLU, EPI_GLU, EPI_QKV, EPI_CONVT, EPI_CONVT_RGB = range(7)
+EPI_STORE, EPI_RESIDUAL, EPI_GEGLU, EPI_GLU, EPI_QKV, EPI_CONVT, EPI_CONVT_RGB, EPI_LNFOLD_RESIDUAL = range(8)
 
 vp, i32, i64, f32, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
 
@@ -19,6 +19,7 @@ class EpilogueArgs(C.Structure):
                 ("heads", i32), ("tokens", i32), ("q_rows", i32), ("kv_rows", i32), ("key_off", i32),
                 ("nq_heads", i32), ("nk_heads", i32), ("nv_heads", i32),
                 ("H", i32), ("W", i32), ("py", i32), ("px", i32),
+                ("row_stats", vp), ("ln_width", i32), ("_pad0", i32),
                 ("rgb_w", vp), ("rgb_b", vp), ("rgb_channels", i32), ("_pad", i32)]
 
 
@@ -48,7 +49,7 @@ class GroupNormArgs(C.Structure):
 
 
 class LayerNormArgs(C.Structure):
-    _fields_ = [("x", vp), ("x_dtype", i32), ("y_dtype", i32), ("y", vp), ("gamma", vp), ("add", vp), ("x_out", vp),
+    _fields_ = [("x", vp), ("x_dtype", i32), ("y_dtype", i32), ("y", vp), ("gamma", vp), ("add", vp), ("x_out", vp), ("zero_stats", vp),
                 ("rows", i64), ("width", i64), ("ldx", i64), ("ldy", i64)]
 
 

@@ -182,10 +182,11 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
                 const int j = j0 + i + e;
                 const bool live = j < p.Tk && (j == 0 || !km || km[j - 1]);
                 pv[e] = live ? exp2f(fmaf(s[i + e], p.scale_log2e, -mneg)) : 0.f;
-                row_sum += pv[e];
               }
               __nv_bfloat162 t = __floats2bfloat162_rn(pv[0], pv[1]);
               packed[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+              const float2 pr = __bfloat1622float2(t);     // normalise by the sum of the ROUNDED weights: O = sum(p~ v) / sum(p~)
+              row_sum += pr.x + pr.y;
             }
             // P[r, c .. c+31] -> sub-tile (c / 64), 16-byte chunks (c % 64) / 8 .. +3, 128B swizzle: chunk ^= (r & 7)
             uint8_t* tile = sP + (c >> 6) * 16384 + r * 128;

@@ -12,10 +12,11 @@ constexpr int LN_MAXV = 16;   // float4 chunks per lane -> width <= 2048
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ add,
-                 float* __restrict__ x_out, int64_t rows, int width, int64_t ldx, int64_t ldy) {
+                 float* __restrict__ x_out, float* __restrict__ zero_stats, int64_t rows, int width, int64_t ldx, int64_t ldy) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (zero_stats && lane == 0) *reinterpret_cast<float2*>(zero_stats + 2 * row) = make_float2(0.f, 0.f);
   const TX* xr = x + row * ldx;
   float v[LN_MAXV * 4];
   float sum = 0.f;
@@ -93,11 +94,12 @@ template <> __device__ __forceinline__ void store_vec<bf16, 4>(bf16* p, const fl
 template <typename TX, typename TY, int CH>
 __global__ void __launch_bounds__(256)
 layernorm_vec_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ add,
-                     float* __restrict__ x_out, int64_t rows, int width, int64_t ldx, int64_t ldy) {
+                     float* __restrict__ x_out, float* __restrict__ zero_stats, int64_t rows, int width, int64_t ldx, int64_t ldy) {
   constexpr int VN = VecIO<TX>::N;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (zero_stats && lane == 0) *reinterpret_cast<float2*>(zero_stats + 2 * row) = make_float2(0.f, 0.f);
   const TX* xr = x + row * ldx;
   float v[CH][VN];
   float sum = 0.f;
@@ -313,10 +315,10 @@ extern "C" int mmg_layernorm(const mmg_layernorm_args* a, void* stream) {
   const bool vec = (a->ldx % vn == 0) && (a->ldy % vn == 0) && ((reinterpret_cast<uintptr_t>(a->x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a->y) & 15) == 0) &&
                    (!a->add || (w % vn == 0 && (reinterpret_cast<uintptr_t>(a->add) & 15) == 0)) && (!a->x_out || w % vn == 0) &&
                    ((w + vn - 1) / vn * vn <= a->ldx) && span <= 16 * 32 * vn;
-#define LNV(TX, TY, CH) layernorm_vec_kernel<TX, TY, CH><<<grid, 256, 0, st>>>((const TX*)a->x, (TY*)a->y, a->gamma, a->add, a->x_out, a->rows, w, a->ldx, a->ldy)
+#define LNV(TX, TY, CH) layernorm_vec_kernel<TX, TY, CH><<<grid, 256, 0, st>>>((const TX*)a->x, (TY*)a->y, a->gamma, a->add, a->x_out, a->zero_stats, a->rows, w, a->ldx, a->ldy)
 #define LNV_DISPATCH(TX, TY) do { const int64_t per = 32 * vn; const int ch = (int)((span + per - 1) / per); \
     if (ch <= 4) LNV(TX, TY, 4); else if (ch <= 6) LNV(TX, TY, 6); else if (ch <= 8) LNV(TX, TY, 8); else LNV(TX, TY, 16); } while (0)
-#define LN_LAUNCH(TX, TY) layernorm_kernel<TX, TY><<<grid, 256, 0, st>>>((const TX*)a->x, (TY*)a->y, a->gamma, a->add, a->x_out, a->rows, w, a->ldx, a->ldy)
+#define LN_LAUNCH(TX, TY) layernorm_kernel<TX, TY><<<grid, 256, 0, st>>>((const TX*)a->x, (TY*)a->y, a->gamma, a->add, a->x_out, a->zero_stats, a->rows, w, a->ldx, a->ldy)
   if (a->x_dtype == MMG_F32 && a->y_dtype == MMG_F32) { if (vec) LNV_DISPATCH(float, float); else LN_LAUNCH(float, float); }
   else if (a->x_dtype == MMG_F32 && a->y_dtype == MMG_BF16) { if (vec) LNV_DISPATCH(float, bf16); else LN_LAUNCH(float, bf16); }
   else if (a->x_dtype == MMG_BF16 && a->y_dtype == MMG_BF16) { if (vec) LNV_DISPATCH(bf16, bf16); else LN_LAUNCH(bf16, bf16); }

@@ -11,6 +11,8 @@ struct Epilogue {
   int fast;                 // 1: tensor-core (bf16) path — MUFU-based erf/sigmoid are accurate far beyond bf16 output precision
   int64_t M, N;
   float rgb_acc[4];
+  float st_a, st_b;         // GEGLU: partial (sum, sumsq) of this thread's outputs; LNFOLD: (mean, rstd) of the row
+  int r_b, r_t;             // QKV: (batch, token) of the row; CONVT*: (batch, y * W + x)
 
   template <typename T>
   static __device__ __forceinline__ void store_n(T* dst, const float* v, int n, bool vec_ok) {
@@ -36,7 +38,15 @@ struct Epilogue {
     }
   }
 
-  __device__ __forceinline__ void begin_row(int64_t) {
+  __device__ __forceinline__ void begin_row(int64_t row) {
+    if (kind == MMG_EPI_QKV) { const uint32_t r = (uint32_t)row, d = (uint32_t)p.tokens; r_b = (int)(r / d); r_t = (int)(r - (uint32_t)r_b * d); }
+    if (kind == MMG_EPI_CONVT || kind == MMG_EPI_CONVT_RGB) { const uint32_t r = (uint32_t)row, d = (uint32_t)(p.H * p.W); r_b = (int)(r / d); r_t = (int)(r - (uint32_t)r_b * d); }
+    if (kind == MMG_EPI_GEGLU) { st_a = 0.f; st_b = 0.f; }
+    if (kind == MMG_EPI_LNFOLD_RESIDUAL) {
+      const float2 s = *reinterpret_cast<const float2*>(p.row_stats + 2 * row);
+      const float mean = s.x / (float)p.ln_width;
+      st_a = mean; st_b = rsqrtf(fmaxf(s.y / (float)p.ln_width - mean * mean, 0.f) + 1e-5f);
+    }
     if (kind == MMG_EPI_CONVT_RGB) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) rgb_acc[c] = (c < p.rgb_channels) ? p.rgb_b[c] : 0.f;
@@ -44,9 +54,21 @@ struct Epilogue {
   }
 
   // row: global output row (< M). col0: first accumulator column of this chunk (multiple of 64). nvalid: columns < N.
+  template <bool FAST>
   __device__ __forceinline__ void apply(int64_t row, int col0, float (&v)[64], int nvalid) {
     const bool bf = (p.out_dtype == MMG_BF16);
     switch (kind) {
+      case MMG_EPI_LNFOLD_RESIDUAL: {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = st_b * (v[i] - st_a * __ldg(p.bias + col0 + i));
+        float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+        const float* r = reinterpret_cast<const float*>(p.resid) + row * p.ldr + col0;
+        float t[64]; Vec64<float>::load(r, t);
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] += t[i];
+        Vec64<float>::store(o, v);
+        break;
+      }
       case MMG_EPI_STORE:
       case MMG_EPI_RESIDUAL: {
         if (p.bias) {
@@ -89,13 +111,17 @@ struct Epilogue {
         float o[32];
         if (kind == MMG_EPI_GEGLU) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = v[32 + i] * (fast ? gelu_fast(v[i]) : gelu_erf(v[i]));
+          for (int i = 0; i < 32; ++i) o[i] = v[32 + i] * (FAST ? gelu_fast(v[i]) : gelu_erf(v[i]));
+          if (p.row_stats) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { st_a += o[i]; st_b = fmaf(o[i], o[i], st_b); }
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             float a = v[i] + (p.bias ? __ldg(p.bias + col0 + i) : 0.f);
             float g = v[32 + i] + (p.bias ? __ldg(p.bias + col0 + 32 + i) : 0.f);
-            o[i] = a * (1.0f / (1.0f + expf(-g)));
+            o[i] = FAST ? a * rcp_fast(1.0f + ex2_fast(-g * 1.4426950408889634f)) : a * (1.0f / (1.0f + expf(-g)));
           }
         }
         const int oc = col0 >> 1;
@@ -120,7 +146,7 @@ struct Epilogue {
       }
       case MMG_EPI_QKV: {
         const int hc = col0 >> 6;
-        const int64_t b = row / p.tokens, t = row - b * p.tokens;
+        const int64_t b = r_b, t = r_t;
         void* dst; int h; int64_t off;
         const float* sc = nullptr;
         if (hc < p.nq_heads) { h = hc; dst = p.q_out; off = ((b * p.heads + h) * (int64_t)p.q_rows + t) * 64; sc = p.q_scale; }
@@ -130,7 +156,7 @@ struct Epilogue {
           float ss = 0.f;
 #pragma unroll
           for (int i = 0; i < 64; ++i) ss += v[i] * v[i];
-          const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+          const float inv = FAST ? rsqrtf(fmaxf(ss, 1e-24f)) : 1.0f / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
           for (int i = 0; i < 64; ++i) v[i] = v[i] * inv * sc[i];
         }
@@ -160,8 +186,7 @@ struct Epilogue {
 #pragma unroll
         for (int i = 0; i < 64; ++i) v[i] = leaky01(v[i] + (p.bias ? __ldg(p.bias + col0 + i) : 0.f));
         if (kind == MMG_EPI_CONVT) {
-          const int64_t hw = (int64_t)p.H * p.W;
-          const int64_t b = row / hw; const int rem = (int)(row - b * hw); const int y = rem / p.W, x = rem - y * p.W;
+          const int64_t b = r_b; const int rem = r_t; const int y = rem / p.W, x = rem - y * p.W;
           const int64_t opix = (b * 2 * p.H + 2 * y + p.py) * (int64_t)(2 * p.W) + 2 * x + p.px;
           const bool vec_ok = (nvalid == 64) && ((p.ldo & 7) == 0);
           if (bf) store_n(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + col0, v, nvalid, vec_ok);
@@ -183,10 +208,32 @@ struct Epilogue {
     }
   }
 
+  // ---- residual epilogues with the residual chunk prefetched by the caller (tensor-core kernel) -------------------------
+  __device__ __forceinline__ bool can_prefetch_resid() const {
+    if (kind == MMG_EPI_LNFOLD_RESIDUAL) return true;
+    return kind == MMG_EPI_RESIDUAL && p.out_dtype == MMG_F32 && (p.ldo & 7) == 0 && (p.ldr & 7) == 0 && p.act == 0;
+  }
+  __device__ __forceinline__ void load_resid(int64_t row, int col0, float (&r)[64]) const {
+    Vec64<float>::load(reinterpret_cast<const float*>(p.resid) + row * p.ldr + col0, r);
+  }
+  // v <- epilogue(v) + r   (r = resid[row, col0 .. col0+63]); the caller stores v with store_f32
+  __device__ __forceinline__ void fuse_resid(int col0, float (&v)[64], const float (&r)[64]) const {
+    if (kind == MMG_EPI_LNFOLD_RESIDUAL) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = fmaf(st_b, v[i] - st_a * __ldg(p.bias + col0 + i), r[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] += r[i] + (p.bias ? __ldg(p.bias + col0 + i) : 0.f);
+    }
+  }
+  __device__ __forceinline__ void store_f32(int64_t row, int col0, const float (&v)[64]) const {
+    Vec64<float>::store(reinterpret_cast<float*>(p.out) + row * p.ldo + col0, v);
+  }
+
   __device__ __forceinline__ void end_row(int64_t row) {
+    if (kind == MMG_EPI_GEGLU && p.row_stats) { atomicAdd(p.row_stats + 2 * row, st_a); atomicAdd(p.row_stats + 2 * row + 1, st_b); }
     if (kind == MMG_EPI_CONVT_RGB) {
-      const int64_t hw = (int64_t)p.H * p.W;
-      const int64_t b = row / hw; const int rem = (int)(row - b * hw); const int y = rem / p.W, x = rem - y * p.W;
+      const int64_t b = r_b; const int rem = r_t; const int y = rem / p.W, x = rem - y * p.W;
       const int oy = 2 * y + p.py, ox = 2 * x + p.px;
       float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
@@ -201,6 +248,10 @@ inline int validate_epilogue(int kind, const mmg_epilogue_args& e, int64_t N) {
   switch (kind) {
     case MMG_EPI_STORE: MMG_CHECK_ARG(e.out, "epilogue STORE: out is NULL"); break;
     case MMG_EPI_RESIDUAL: MMG_CHECK_ARG(e.out && e.resid, "epilogue RESIDUAL: out/resid NULL"); break;
+    case MMG_EPI_LNFOLD_RESIDUAL:
+      MMG_CHECK_ARG(e.out && e.resid && e.bias && e.row_stats && e.ln_width > 0, "epilogue LNFOLD_RESIDUAL: out/resid/cvec/row_stats/ln_width");
+      MMG_CHECK_ARG(e.out_dtype == MMG_F32 && (N % 64) == 0 && (e.ldo % 4) == 0 && (e.ldr % 4) == 0, "epilogue LNFOLD_RESIDUAL: fp32 out, N %% 64, ld %% 4");
+      break;
     case MMG_EPI_GEGLU: case MMG_EPI_GLU: MMG_CHECK_ARG(e.out && (N % 64) == 0, "epilogue GEGLU/GLU: N %% 64 != 0 or out NULL"); break;
     case MMG_EPI_QKV:
       MMG_CHECK_ARG((N % 64) == 0 && N / 64 == e.nq_heads + e.nk_heads + e.nv_heads, "epilogue QKV: N != 64*(nq+nk+nv)");

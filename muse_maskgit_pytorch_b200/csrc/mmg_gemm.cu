@@ -107,7 +107,7 @@ simt_gemm_kernel(const T* __restrict__ A, const T* __restrict__ Wt, int64_t M, i
       int nvalid = (int)(N - n0); if (nvalid > 64) nvalid = 64;
       // CONVT_RGB needs the whole row in one pass and is not offered on this path (validated by the launcher)
       epi.begin_row(row);
-      epi.apply(row, n0, v, nvalid);
+      epi.template apply<false>(row, n0, v, nvalid);
       epi.end_row(row);
     }
   }

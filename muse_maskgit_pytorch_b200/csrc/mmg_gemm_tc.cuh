@@ -2,8 +2,9 @@
 //
 //   warp 0      : TMA producer  (one elected lane) — A tile 128x64 and W tile BNx64 per k-block, SWIZZLE_128B
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane) — 4 x tcgen05.mma (K=16) per k-block, M=128, N=BN
-//   warps 2..9  : epilogue — tcgen05.ld (32 lanes x 32 cols) -> registers -> fused Epilogue -> global; two warps share a TMEM
-//                 lane quarter and take alternate 64-column chunks
+//   warps 4..11 : epilogue — tcgen05.ld (32 lanes x 32 cols) -> registers -> fused Epilogue -> global; two warps share a TMEM
+//                 lane quarter and take alternate 64-column chunks.  setmaxnreg moves registers from warpgroup 0 (40/thread)
+//                 to the epilogue warpgroups (232/thread) so a residual chunk can be prefetched while the MMA is in flight.
 //   persistent grid (<= #SM CTAs), static tile schedule, STAGES-deep smem ring, 2 accumulator stages in TMEM so the
 //   epilogue of tile i overlaps the main loop of tile i+1.
 //
@@ -19,7 +20,7 @@ namespace mmg {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int TC_THREADS = 384;          // warpgroup 0: warp 0 TMA, warp 1 MMA (2, 3 idle); warpgroups 1-2: 8 epilogue warps
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_MAX_TAPS = 16;
 
@@ -81,6 +82,8 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
@@ -135,14 +138,17 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     // ===================== epilogue warps =====================
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access (warp id % 4)
-    const int half = (warp - 2) >> 2;             // 0: even 64-column chunks, 1: odd chunks
+    const int half = (warp - 4) >> 2;             // 0: even 64-column chunks, 1: odd chunks
     const int r_in_tile = quarter * 32 + lane;
     Epilogue epi = p.epi;
     if (epi.kind == MMG_EPI_QKV) { epi.p.q_scale = s_scale; epi.p.k_scale = s_scale + 64; }
     const bool whole_row = (epi.kind == MMG_EPI_CONVT_RGB);      // needs every chunk of a row in one thread
+    const bool prefetch_resid = epi.can_prefetch_resid();
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % p.num_m_tiles, n_blk = tile / p.num_m_tiles;
@@ -156,20 +162,33 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         valid = b < p.B;
         row = ((int64_t)b * p.Ho + (yt * p.TH + ty)) * p.Wo + xt * p.TW + tx;
       }
+      const bool mine = !whole_row || half == 0;
+      const int c_first = whole_row ? 0 : half, c_step = whole_row ? 1 : 2;
+      const bool pre = prefetch_resid && valid && mine && (n_blk * BN + c_first * 64 < p.N) && c_first < BN / 64;
+      float rbuf[64];
+      if (pre) epi.load_resid(row, n_blk * BN + c_first * 64, rbuf);      // in flight while the MMA of this tile completes
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      const bool mine = !whole_row || half == 0;
       if (valid && mine) epi.begin_row(row);
 #pragma unroll 1
-      for (int c = (whole_row ? 0 : half); c < BN / 64; c += (whole_row ? 1 : 2)) {
+      for (int c = c_first; c < BN / 64; c += c_step) {
         if (!mine) break;
         float v[64];
         tmem_ld_32x32b_x32(t_row + c * 64, v);
         tmem_ld_32x32b_x32(t_row + c * 64 + 32, v + 32);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 64;
-        if (valid && col0 < p.N) epi.apply(row, col0, v, 64);
+        if (valid && col0 < p.N) {
+          if (prefetch_resid) {
+            epi.fuse_resid(col0, v, rbuf);
+            const int cn = col0 + c_step * 64;
+            if (c + c_step < BN / 64 && cn < p.N) epi.load_resid(row, cn, rbuf);   // next chunk's residual overlaps the stores
+            epi.store_f32(row, col0, v);
+          } else {
+            epi.template apply<true>(row, col0, v, 64);
+          }
+        }
       }
       if (valid && mine) epi.end_row(row);
       tc_fence_before();

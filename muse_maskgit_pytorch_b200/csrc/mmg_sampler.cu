@@ -98,15 +98,11 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   }
   if (tid == 0) s_count = 0;
   float tlo;
-  {
-    int rs;
-    if (ns == V) rs = k;
-    else { const float pf = (float)k / (float)V; const float mu = pf * ns; rs = (int)(mu + 4.5f * sqrtf(mu * (1.f - pf)) + 2.f); }
-    if (rs > ns) rs = ns;
-    // radix descent, two key bits per round: largest t with count(key >= t) >= rs (sampled rows: 20 bits suffice for a lower bound)
+  if (ns == V) {
+    // small rows: the "sample" is the whole row -> exact k-th largest by a block-wide radix descent (two key bits per round)
+    const int rs = k < ns ? k : ns;
     uint32_t prefix = 0;
-    const int last = (ns == V) ? 0 : 12;
-    for (int bit = 30; bit >= last; bit -= 2) {
+    for (int bit = 30; bit >= 0; bit -= 2) {
       const uint32_t c1 = prefix | (1u << bit), c2 = prefix | (2u << bit), c3 = prefix | (3u << bit);
       int n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
@@ -118,24 +114,56 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
     }
     tlo = key_to_float(prefix);
     if (prefix == 0) tlo = -FLT_MAX;
+  } else {
+    // sampled rows: every warp finds the rank-(rs/16) key of ITS 256 samples with shuffles only (no block barrier), the block
+    // threshold is the mean of the 16 warp estimates (same variance as one 4096-sample quantile; exactness is restored below)
+    const float pf = (float)k / (float)V; const float mu = pf * ns;
+    const int rs = (int)(mu + 4.5f * sqrtf(mu * (1.f - pf)) + 2.f);
+    const int rw = (rs + SMP_THREADS / 32 - 1) / (SMP_THREADS / 32);
+    uint32_t prefix = 0;
+    for (int bit = 30; bit >= 12; bit -= 2) {                          // 20 key bits are plenty for a lower bound
+      const uint32_t c1 = prefix | (1u << bit), c2 = prefix | (2u << bit), c3 = prefix | (3u << bit);
+      int n = 0;
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) n += (sk[j] >= c1) + ((sk[j] >= c2) << 10) + ((sk[j] >= c3) << 20);
+      n = __reduce_add_sync(0xffffffffu, n);
+      const int t1 = n & 1023, t2 = (n >> 10) & 1023, t3 = n >> 20;
+      if (t3 >= rw) prefix = c3; else if (t2 >= rw) prefix = c2; else if (t1 >= rw) prefix = c1;
+    }
+    if (lane == 0) s_redf[warp] = prefix ? key_to_float(prefix) : -FLT_MAX;
+    __syncthreads();
+    float acc = 0.f; bool bad = false;
+#pragma unroll
+    for (int w = 0; w < SMP_THREADS / 32; ++w) { const float t = s_redf[w]; bad |= (t == -FLT_MAX) | !(t == t); acc += t; }
+    tlo = bad ? -FLT_MAX : acc * (1.0f / (SMP_THREADS / 32));
+    __syncthreads();
   }
   const bool degenerate = (tlo == -FLT_MAX);                         // no usable threshold: every element is a candidate (-> exact rebuild)
 
   // ---------------- phase B: one streaming pass over the row ----------------
   constexpr float LOG2E = 1.4426950408889634f;
-  float m_t = -FLT_MAX, s_t = 0.f;                                 // running max and sum of 2^((x - m) * log2e)
+  constexpr float NEG_BIG = -1e30f;                                // "minus infinity" that stays finite after * log2e
+  float m_t = NEG_BIG, s_t = 0.f;                                  // running max and sum of 2^((x - m) * log2e)
   if ((V & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
     const float4* r4 = reinterpret_cast<const float4*>(row);
     const int n4 = V >> 2;
-    constexpr int UNR = 4;                                          // 4 independent 128-bit loads in flight per thread
+    constexpr int UNR = 4;                                          // 4 independent 128-bit loads per thread, next group prefetched
+    float4 nxt[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int i = u * SMP_THREADS + tid;
+      nxt[u] = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
+      if (i < n4) nxt[u] = ld_stream4(r4 + i);
+    }
     for (int i0 = 0; i0 < n4; i0 += SMP_THREADS * UNR) {
       float xs[UNR * 4];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int i = i0 + u * SMP_THREADS + tid;
-        float4 q = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-        if (i < n4) q = ld_stream4(r4 + i);
-        xs[4 * u] = q.x; xs[4 * u + 1] = q.y; xs[4 * u + 2] = q.z; xs[4 * u + 3] = q.w;
+      for (int u = 0; u < UNR; ++u) { xs[4 * u] = nxt[u].x; xs[4 * u + 1] = nxt[u].y; xs[4 * u + 2] = nxt[u].z; xs[4 * u + 3] = nxt[u].w; }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {                                // prefetch the following group while this one is processed
+        const int i = i0 + SMP_THREADS * UNR + u * SMP_THREADS + tid;
+        nxt[u] = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
+        if (i < n4) nxt[u] = ld_stream4(r4 + i);
       }
       float lm = xs[0];
 #pragma unroll
@@ -144,7 +172,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
       const float mb = m_t * LOG2E;
       int c = 0;
 #pragma unroll
-      for (int j = 0; j < UNR * 4; ++j) {                            // padding lanes hold -FLT_MAX: contribute 2^-inf = 0
+      for (int j = 0; j < UNR * 4; ++j) {                            // padding lanes hold -1e30: contribute 2^-huge = 0
         s_t += ex2_approx(fmaf(xs[j], LOG2E, -mb));
         c += ((xs[j] >= tlo) | degenerate) & (i0 + (j >> 2) * SMP_THREADS + tid < n4);
       }
@@ -173,7 +201,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   } else {
     for (int i0 = 0; i0 < V; i0 += SMP_THREADS) {
       const int i = i0 + tid;
-      float x = -FLT_MAX; int c = 0;
+      float x = NEG_BIG; int c = 0;
       if (i < V) {
         x = ld_stream(row + i);
         if (x > m_t) { s_t *= ex2_approx((m_t - x) * LOG2E); m_t = x; }

@@ -121,7 +121,12 @@ class Transformer(nn.Module):
             w1p[dst_x[valid] + 32] = w1[F_:]
             g3 = torch.zeros(Fp, device=dev); g3[:F_] = ff[3].gamma.detach().float()
             w2 = torch.zeros((ff[4].weight.shape[0], Fp), device=dev); w2[:, :F_] = ff[4].weight.detach().float()
-            return dict(F=F_, Fp=Fp, g0=f32(ff[0].gamma), w1=w1p.to(adt).contiguous(), g3=g3.contiguous(), w2=w2.to(adt).contiguous())
+            out = dict(F=F_, Fp=Fp, g0=f32(ff[0].gamma), w1=w1p.to(adt).contiguous(), g3=g3.contiguous(), w2=w2.to(adt).contiguous())
+            if adt == torch.bfloat16:
+                # LayerNorm(inner) folded through the second linear: LN(h) W2^T = rstd * (h (W2*gamma)^T - mean * cvec), cvec = rowsum(W2*gamma)
+                w2f = (w2 * g3[None, :]).to(adt).contiguous()
+                out["w2f"], out["cvec"] = w2f, w2f.float().sum(dim=1).contiguous()
+            return out
 
         for attn, cross, ff in tb.layers:
             h = attn.heads
@@ -213,7 +218,8 @@ class Transformer(nn.Module):
                   v=torch.zeros((nb * b * heads, tk_alloc, 64), device=dev, dtype=adt),
                   ao=torch.empty((R, inner), device=dev, dtype=adt),
                   h=torch.empty((R, Fp), device=dev, dtype=adt),
-                  hn=torch.empty((R, Fp), device=dev, dtype=adt))
+                  hn=torch.empty((R, Fp), device=dev, dtype=adt),
+                  stats=torch.zeros((R, 2), device=dev, dtype=torch.float32))
         self._ws = ws
         return ws
 
@@ -260,17 +266,25 @@ class Transformer(nn.Module):
             # --- feed forward (the constant null-branch cross-attention term is folded into this LayerNorm) ---
             for j in range(nb):
                 xs = x[j * bn:(j + 1) * bn]
+                zs = ws["stats"][j * bn:(j + 1) * bn]          # row statistics of the GEGLU output, reset here, accumulated by FF1's epilogue
                 if j in pending_add:
-                    ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn], add=pending_add[j], x_out=xs)
+                    ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn], add=pending_add[j], x_out=xs, zero_stats=zs)
                 else:
-                    ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn])
+                    ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn], zero_stats=zs)
             self._ff_tail(xn, ff, x, ws, R)
         return x
 
-    def _ff_tail(self, xn, ff, x, ws, R):
+    def _ff_tail(self, xn, ff, x, ws, R, stats_zeroed=True):
         h, hn = ws["h"][:R, :ff["Fp"]], ws["hn"][:R, :ff["Fp"]]
         if ff["Fp"] != ws["h"].shape[1]:
             h, hn = h.contiguous(), hn.contiguous()
+        if "w2f" in ff:      # bf16: inner LayerNorm folded into the two GEMM epilogues (no pass over h between them)
+            stats = ws["stats"][:R]
+            if not stats_zeroed:
+                stats.zero_()
+            ops.linear(xn[:R], ff["w1"], h, epilogue=ops.EPI_GEGLU, row_stats=stats)
+            ops.linear(h, ff["w2f"], x[:R], epilogue=ops.EPI_LNFOLD_RESIDUAL, bias=ff["cvec"], resid=x[:R], row_stats=stats, ln_width=ff["F"])
+            return
         ops.linear(xn[:R], ff["w1"], h, epilogue=ops.EPI_GEGLU)
         ops.layernorm(h, ff["g3"], hn, width=ff["F"])
         ops.linear(hn, ff["w2"], x[:R], epilogue=ops.EPI_RESIDUAL, resid=x[:R])
@@ -278,7 +292,7 @@ class Transformer(nn.Module):
     def _ff(self, inp, ff, x_acc, ws, R):
         """x_acc += FeedForward(inp)   (self-conditioning embed, muse_maskgit_pytorch.py:325-328)"""
         xn = ws["xn"][:R]
-        ops.layernorm(inp, ff["g0"], xn)
+        ops.layernorm(inp, ff["g0"], xn, zero_stats=ws["stats"][:R])
         self._ff_tail(xn, ff, x_acc, ws, R)
 
     # ----- public API ---------------------------------------------------------------------------------------------------

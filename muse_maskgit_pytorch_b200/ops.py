@@ -3,7 +3,8 @@ memory and the stream; every number is computed by libmmg.so."""
 import torch
 
 from . import _lib as L
-from ._lib import F32, BF16, EPI_STORE, EPI_RESIDUAL, EPI_GEGLU, EPI_GLU, EPI_QKV, EPI_CONVT, EPI_CONVT_RGB  # noqa: F401
+from ._lib import (F32, BF16, EPI_STORE, EPI_RESIDUAL, EPI_GEGLU, EPI_GLU, EPI_QKV, EPI_CONVT, EPI_CONVT_RGB,  # noqa: F401
+                   EPI_LNFOLD_RESIDUAL)
 
 
 def _chk(t, name="tensor"):
@@ -11,8 +12,9 @@ def _chk(t, name="tensor"):
     return t
 
 
-def _epi(out=None, ldo=0, bias=None, act=0, resid=None, ldr=0):
+def _epi(out=None, ldo=0, bias=None, act=0, resid=None, ldr=0, row_stats=None, ln_width=0):
     e = L.EpilogueArgs()
+    e.row_stats = L.ptr(row_stats); e.ln_width = ln_width
     if out is not None:
         e.out = out.data_ptr(); e.ldo = ldo; e.out_dtype = L.dt(out)
     e.act = act
@@ -22,7 +24,7 @@ def _epi(out=None, ldo=0, bias=None, act=0, resid=None, ldr=0):
     return e
 
 
-def linear(a, w, out, epilogue=EPI_STORE, bias=None, act=0, resid=None, M=None, N=None, epi=None):
+def linear(a, w, out, epilogue=EPI_STORE, bias=None, act=0, resid=None, M=None, N=None, epi=None, row_stats=None, ln_width=0):
     """out = a @ w.T (+ epilogue).  a [M, K], w [N, K] same dtype (bf16 -> tcgen05, fp32 -> CUDA cores)."""
     _chk(a, "a"); _chk(w, "w")
     args = L.LinearArgs()
@@ -33,7 +35,7 @@ def linear(a, w, out, epilogue=EPI_STORE, bias=None, act=0, resid=None, M=None, 
     assert w.shape[1] == a.shape[1] and a.dtype == w.dtype
     args.dtype = L.dt(a); args.epilogue = epilogue
     if epi is None:
-        epi = _epi(out, out.stride(0), bias, act, resid, resid.stride(0) if resid is not None else 0)
+        epi = _epi(out, out.stride(0), bias, act, resid, resid.stride(0) if resid is not None else 0, row_stats, ln_width)
     args.epi = epi
     L.call("mmg_linear", args)
     return out
@@ -101,8 +103,9 @@ def groupnorm_(x, gamma, beta, B, HW, Cch, groups=16, act=0):
     return x
 
 
-def layernorm(x, gamma, y, width=None, add=None, x_out=None, rows=None):
+def layernorm(x, gamma, y, width=None, add=None, x_out=None, rows=None, zero_stats=None):
     a = L.LayerNormArgs()
+    a.zero_stats = L.ptr(zero_stats)
     a.x = _chk(x).data_ptr(); a.x_dtype = L.dt(x); a.y = _chk(y).data_ptr(); a.y_dtype = L.dt(y)
     a.gamma = gamma.data_ptr(); a.add = L.ptr(add); a.x_out = L.ptr(x_out)
     a.rows = x.shape[0] if rows is None else rows

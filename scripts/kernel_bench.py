@@ -52,7 +52,8 @@ def want(k):
 R = 2 * 64 * 256            # rows of a CFG decode step at B=64
 if want("gemm"):
     for name, M, N, K, epi in [("qkv  M=32768 N=1536 K=512", R, 1536, 512, "store_bf16"), ("wo   M=32768 N=512 K=512 +resid", R, 512, 512, "resid"),
-                               ("ff1  M=32768 N=2816 K=512 geglu", R, 2816, 512, "geglu"), ("ff2  M=32768 N=512 K=1408 +resid", R, 512, 1408, "resid"),
+                               ("ff1  M=32768 N=2816 K=512 geglu", R, 2816, 512, "geglu"), ("ff1  M=32768 N=2816 K=512 geglu+rowstats", R, 2816, 512, "geglu_stats"),
+                               ("ff2  M=32768 N=512 K=1408 +resid", R, 512, 1408, "resid"), ("ff2  M=32768 N=512 K=1408 lnfold+resid", R, 512, 1408, "lnfold"),
                                ("logits M=10240 N=65536 K=512 fp32 out", 10240, 65536, 512, "store_f32"), ("logits M=16384 N=65536 K=512 fp32 out", 16384, 65536, 512, "store_f32"),
                                ("logits M=64 N=65536 K=512 fp32 out", 64, 65536, 512, "store_f32"), ("square 8192^3 bf16 out", 8192, 8192, 8192, "store_bf16")]:
         a = torch.randn((M, K), device="cuda").to(bf); w = (torch.randn((N, K), device="cuda") * K ** -0.5).to(bf)
@@ -62,6 +63,11 @@ if want("gemm"):
             out = torch.empty((M, N), device="cuda"); fn = lambda: ops.linear(a, w, out)
         elif epi == "resid":
             out = torch.zeros((M, N), device="cuda"); fn = lambda: ops.linear(a, w, out, epilogue=ops.EPI_RESIDUAL, resid=out)
+        elif epi == "geglu_stats":
+            out = torch.empty((M, N // 2), device="cuda", dtype=bf); st = torch.zeros((M, 2), device="cuda"); fn = lambda: ops.linear(a, w, out, epilogue=ops.EPI_GEGLU, row_stats=st)
+        elif epi == "lnfold":
+            out = torch.zeros((M, N), device="cuda"); st = torch.ones((M, 2), device="cuda") * 1365; cv = torch.zeros(N, device="cuda")
+            fn = lambda: ops.linear(a, w, out, epilogue=ops.EPI_LNFOLD_RESIDUAL, bias=cv, resid=out, row_stats=st, ln_width=1365)
         else:
             out = torch.empty((M, N // 2), device="cuda", dtype=bf); e = ops._epi(out, N // 2); fn = lambda: ops.linear(a, w, None, epilogue=ops.EPI_GEGLU, epi=e)
         report("gemm " + name, timeit(fn), flops=2.0 * M * N * K)
@@ -93,7 +99,8 @@ if want("attn"):
         v = torch.zeros_like(k); v[:, :Tk] = torch.randn((B * heads, Tk, 64), device="cuda").to(bf)
         out = torch.empty((B * Tq, heads * 64), device="cuda", dtype=bf)
         km = (torch.rand((B, Tk - 1), device="cuda") > 0.2).to(torch.uint8) if masked else None
-        report("attention " + name, timeit(lambda: ops.attention(q, k, v, out, B, heads, Tk, key_mask=km)), flops=4.0 * B * heads * Tq * Tk * 64)
+        report("attention " + name + " two-pass", timeit(lambda: ops.attention(q, k, v, out, B, heads, Tk, key_mask=km)), flops=4.0 * B * heads * Tq * Tk * 64)
+        report("attention " + name + " single-pass", timeit(lambda: ops.attention(q, k, v, out, B, heads, Tk, key_mask=km, logit_bound=1.02)), flops=4.0 * B * heads * Tq * Tk * 64)
 
 if want("conv"):
     B = 64

@@ -428,3 +428,31 @@ def test_groupnorm_and_conv_in(dtype):
     ops().conv_in(dev(img), dev(w), dev(b), out)
     ok, msg = close(out, nhwc(F.conv2d(img, w, b, padding=2)).reshape(-1, 64), 2e-2 if dtype == torch.bfloat16 else 1e-5, 1e-2)
     assert ok, msg
+
+
+def test_linear_geglu_lnfold_pair():
+    """inner LayerNorm folded through FF2: GEGLU epilogue accumulates per-row (sum, sumsq); LNFOLD_RESIDUAL applies
+    rstd * (acc - mean * cvec) + resid  ==  resid + LN(h) W2^T   (ref: muse_maskgit_pytorch.py:83-89)."""
+    M, K, Fu, Fp, dim = 300, 128, 341, 384, 128
+    bf = torch.bfloat16
+    a = rnd("a", (M, K), bf)
+    wx, wg = rnd("wx", (Fu, K), bf, std=K ** -0.5), rnd("wg", (Fu, K), bf, std=K ** -0.5)
+    wxp, wgp = torch.zeros((Fp, K)), torch.zeros((Fp, K)); wxp[:Fu], wgp[:Fu] = wx, wg
+    w1 = torch.stack((wxp.view(-1, 32, K), wgp.view(-1, 32, K)), 1).reshape(2 * Fp, K)
+    g3 = 1 + 0.1 * rnd("g3", (Fu,))
+    w2 = rnd("w2", (dim, Fu), std=Fu ** -0.5)
+    w2f = torch.zeros((dim, Fp)); w2f[:, :Fu] = w2 * g3
+    w2f = w2f.to(bf)
+    cvec = w2f.float().sum(1)
+    x = rnd("x", (M, dim))
+    h = torch.empty((M, Fp), device="cuda", dtype=bf)
+    stats = torch.zeros((M, 2), device="cuda")
+    xd = dev(x)
+    ops().linear(dev(a, bf), dev(w1, bf), h, epilogue=ops().EPI_GEGLU, row_stats=stats)
+    ops().linear(h, dev(w2f), xd, epilogue=ops().EPI_LNFOLD_RESIDUAL, bias=dev(cvec), resid=xd, row_stats=stats, ln_width=Fu)
+    href = (a @ wg.t()) * F.gelu(a @ wx.t())
+    ok, msg = close(stats[:, 0], href.sum(-1), 2e-3, 1e-3)
+    assert ok, "row sums: " + msg
+    ref = x + F.layer_norm(href, (Fu,), g3, None) @ w2.t()
+    ok, msg = close(xd, ref, 3e-2, 1e-2)
+    assert ok, msg
