@@ -59,6 +59,11 @@ enum mmg_epilogue {
   MMG_EPI_LNFOLD_RESIDUAL = 7, /* LayerNorm folded through the product: with W' = W*gamma, cvec[c] = sum_k W'[c,k] (passed as
                                   `bias`) and per-row (sum, sumsq) of the un-normalised A row in `row_stats`:
                                   out[r,c] = resid[r,c] + rstd_r * (acc - mean_r * cvec[c])   == resid + LN(a_r) W^T           */
+  MMG_EPI_LFQ_IDS    = 8, /* LFQ lookup fused into the projection: W rows = [hi(bits) | mid(bits) | lo(bits)] (a 3-way bf16 split
+                             of the fp32 project_in weight, 3*bits <= 64 = N), bias = project_in bias [bits], ln_width = bits:
+                             ids[r] = sum_i ((hi+mid+lo)_i + bias_i > 0) << (bits-1-i), written as int64 to out[r]                */
+  MMG_EPI_ARGMIN     = 9, /* nearest codebook row: W = codebook [K, D], bias = ||e_k||^2 [K]; out = uint64 best[M], initialised to
+                             all-ones by the caller, updated with atomicMin( orderkey(||e||^2 - 2 x.e) << 32 | k ): lowest k on ties */
 };
 
 typedef struct {
@@ -231,7 +236,8 @@ typedef struct {
 } mmg_vq_lfq_encode_args;
 int mmg_vq_lfq_encode(const mmg_vq_lfq_encode_args* a, void* stream);
 
-/* explicit codebook: ids[t] = argmin_k ||x_t - e_k||^2 (first index on ties); coalesced codebook scan + warp argmin */
+/* explicit codebook: ids[t] = argmin_k ||x_t - e_k||^2 (first index on ties); 64x64 tiles staged through shared memory with
+ * coalesced loads, per-row packed (distance, code) atomicMin across code tiles.  (Large problems: mmg_linear + MMG_EPI_ARGMIN.) */
 typedef struct {
   const float* x; const float* codebook;   /* [T, D], [K, D] fp32                                                  */
   int64_t* ids; int64_t T; int32_t K, D;

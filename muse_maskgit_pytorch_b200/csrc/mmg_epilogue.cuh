@@ -58,6 +58,36 @@ struct Epilogue {
   __device__ __forceinline__ void apply(int64_t row, int col0, float (&v)[64], int nvalid) {
     const bool bf = (p.out_dtype == MMG_BF16);
     switch (kind) {
+      case MMG_EPI_LFQ_IDS: {
+        const int bits = p.ln_width;                 // 3 * bits <= 64: columns [hi | mid | lo] of the split projection
+        long long id = 0;
+#pragma unroll
+        for (int i = 0; i < 21; ++i) {
+          if (i < bits) {
+            float s3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) if (j == i || j == i + bits || j == i + 2 * bits) s3 += v[j];
+            if (s3 + (p.bias ? __ldg(p.bias + i) : 0.f) > 0.f) id |= 1ll << (bits - 1 - i);
+          }
+        }
+        if (col0 == 0) reinterpret_cast<long long*>(p.out)[row] = id;
+        break;
+      }
+      case MMG_EPI_ARGMIN: {
+        unsigned long long best = ~0ull;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          if (i < nvalid) {
+            const float d = __ldg(p.bias + col0 + i) - 2.f * v[i];
+            const uint32_t u = __float_as_uint(d);
+            const uint32_t key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            const unsigned long long cand = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(col0 + i);
+            best = cand < best ? cand : best;
+          }
+        }
+        atomicMin(reinterpret_cast<unsigned long long*>(p.out) + row, best);
+        break;
+      }
       case MMG_EPI_LNFOLD_RESIDUAL: {
 #pragma unroll
         for (int i = 0; i < 64; ++i) v[i] = st_b * (v[i] - st_a * __ldg(p.bias + col0 + i));
@@ -248,6 +278,8 @@ inline int validate_epilogue(int kind, const mmg_epilogue_args& e, int64_t N) {
   switch (kind) {
     case MMG_EPI_STORE: MMG_CHECK_ARG(e.out, "epilogue STORE: out is NULL"); break;
     case MMG_EPI_RESIDUAL: MMG_CHECK_ARG(e.out && e.resid, "epilogue RESIDUAL: out/resid NULL"); break;
+    case MMG_EPI_LFQ_IDS: MMG_CHECK_ARG(e.out && N == 64 && e.ln_width >= 1 && 3 * e.ln_width <= 64, "epilogue LFQ_IDS: N must be 64 and 3*bits <= 64"); break;
+    case MMG_EPI_ARGMIN: MMG_CHECK_ARG(e.out && e.bias, "epilogue ARGMIN: out / code norms NULL"); break;
     case MMG_EPI_LNFOLD_RESIDUAL:
       MMG_CHECK_ARG(e.out && e.resid && e.bias && e.row_stats && e.ln_width > 0, "epilogue LNFOLD_RESIDUAL: out/resid/cvec/row_stats/ln_width");
       MMG_CHECK_ARG(e.out_dtype == MMG_F32 && (N % 64) == 0 && (e.ldo % 4) == 0 && (e.ldr % 4) == 0, "epilogue LNFOLD_RESIDUAL: fp32 out, N %% 64, ld %% 4");

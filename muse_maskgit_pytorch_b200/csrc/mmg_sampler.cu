@@ -35,8 +35,8 @@ __device__ __forceinline__ float4 ld_stream4(const float4* p) {
 __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;     // one IMAD.WIDE each
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
     const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
     c0 = n0; c1 = n1; c2 = n2; c3 = n3;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
@@ -159,24 +159,37 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
       float xs[UNR * 4];
 #pragma unroll
       for (int u = 0; u < UNR; ++u) { xs[4 * u] = nxt[u].x; xs[4 * u + 1] = nxt[u].y; xs[4 * u + 2] = nxt[u].z; xs[4 * u + 3] = nxt[u].w; }
+      const bool full = i0 + SMP_THREADS * UNR <= n4;                 // block-uniform: every thread's 16 elements are in range
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {                                // prefetch the following group while this one is processed
         const int i = i0 + SMP_THREADS * UNR + u * SMP_THREADS + tid;
         nxt[u] = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
         if (i < n4) nxt[u] = ld_stream4(r4 + i);
       }
-      float lm = xs[0];
+      const bool has = full || (i0 + tid) < n4;                      // a thread with no element must not touch the statistics:
+      float lm = xs[0];                                              // fma(-1e30, log2e, -fl(-1e30 * log2e)) is a huge rounding residue
 #pragma unroll
       for (int j = 1; j < UNR * 4; ++j) lm = fmaxf(lm, xs[j]);
-      if (lm > m_t) { s_t *= ex2_approx((m_t - lm) * LOG2E); m_t = lm; }
+      if (has && lm > m_t) { s_t *= ex2_approx((m_t - lm) * LOG2E); m_t = lm; }
       const float mb = m_t * LOG2E;
-      int c = 0;
+      unsigned mask = 0;                                             // bit j: element j of this thread is a top-k candidate
+      if (has) {
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < UNR * 4; ++j) {                            // padding lanes hold -1e30: contribute 2^-huge = 0
-        s_t += ex2_approx(fmaf(xs[j], LOG2E, -mb));
-        c += ((xs[j] >= tlo) | degenerate) & (i0 + (j >> 2) * SMP_THREADS + tid < n4);
+        for (int j = 0; j < UNR * 4; j += 2) {                       // padding lanes hold -1e30: 2^-huge = 0, never >= tlo
+          s0 += ex2_approx(fmaf(xs[j], LOG2E, -mb)); s1 += ex2_approx(fmaf(xs[j + 1], LOG2E, -mb));
+          mask |= (xs[j] >= tlo ? 1u : 0u) << j; mask |= (xs[j + 1] >= tlo ? 1u : 0u) << (j + 1);
+        }
+        s_t += s0 + s1;
+        if (degenerate) {                                            // no usable threshold: everything in range is a candidate
+          mask = 0;
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) if (i0 + u * SMP_THREADS + tid < n4) mask |= 0xFu << (4 * u);
+        }
       }
-      // warp-aggregated append (one shared-memory atomic per warp per 16 elements)
+      // warp-aggregated append of the candidate INDICES (one shared-memory atomic per warp per 16 elements per thread);
+      // the values are re-read from the (L2-resident) row when the list is consumed
+      const int c = __popc(mask);
       int incl = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -185,16 +198,10 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
         int start = 0;
         if (lane == 0) start = atomicAdd(&s_count, tot);
         start = __shfl_sync(0xffffffffu, start, 0) + incl - c;
-        if (c) {
-#pragma unroll
-          for (int u = 0; u < UNR; ++u) {
-            const int i = i0 + u * SMP_THREADS + tid;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float x = xs[4 * u + j];
-              if (i < n4 && ((x >= tlo) | degenerate)) { if (start < SMP_CAP) { lval[start] = x; lidx[start] = i * 4 + j; } ++start; }
-            }
-          }
+        while (mask) {
+          const int j = __ffs(mask) - 1; mask &= mask - 1;
+          if (start < SMP_CAP) lidx[start] = (i0 + (j >> 2) * SMP_THREADS + tid) * 4 + (j & 3);
+          ++start;
         }
       }
     }
@@ -216,7 +223,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
         int start = 0;
         if (lane == 0) start = atomicAdd(&s_count, tot);
         start = __shfl_sync(0xffffffffu, start, 0) + incl - c;
-        if (c && start < SMP_CAP) { lval[start] = x; lidx[start] = i; }
+        if (c && start < SMP_CAP) lidx[start] = i;
       }
     }
   }
@@ -237,6 +244,10 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
     __syncthreads();
   }
   int n = s_n;
+  if (n >= k && n <= SMP_CAP) {                        // candidate values: gather from the row just streamed (L2 hits)
+    for (int sl = tid; sl < n; sl += SMP_THREADS) lval[sl] = row[lidx[sl]];
+    __syncthreads();
+  }
 
   // ---------------- rare: exact rebuild when the sample threshold missed ----------------
   if (n < k || n > SMP_CAP) {

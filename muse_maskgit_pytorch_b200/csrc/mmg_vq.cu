@@ -41,49 +41,64 @@ lfq_encode_kernel(const T* __restrict__ x, const float* __restrict__ w_in, const
   }
 }
 
-// Explicit codebook: ids[t] = argmin_k ||x_t - e_k||^2 = argmin_k (||e_k||^2 - 2 x_t.e_k)  (+||x_t||^2, constant in k).
-// CTA = 8 warps x 4 tokens per warp kept in shared memory; the codebook streams through once per CTA in coalesced
-// 128-bit loads (code k is read by one warp, all 32 lanes across D); warp-shuffle sum, running (min, argmin) per
-// token in registers (first index wins ties), cross-warp argmin at the end.
-constexpr int VQ_TOK = 16;   // tokens per CTA
+// Explicit codebook: ids[t] = argmin_k ||x_t - e_k||^2 = argmin_k (||e_k||^2 - 2 x_t.e_k)   (||x_t||^2 is constant in k).
+// Tiled scan: CTA = 64 tokens x 64 codes, the token and code tiles are staged through shared memory with coalesced loads
+// (16 channels per step), 4x4 register micro-tiles, code norms accumulated on the fly; each row's best (distance, code) of
+// the tile is merged across code tiles with one 64-bit atomicMin on (orderkey(distance) << 32 | code): lowest code wins ties.
+__global__ void vq_init_kernel(unsigned long long* ids, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ids[i] = ~0ull;
+}
+__global__ void vq_finish_kernel(unsigned long long* ids, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ids[i] &= 0xffffffffull;
+}
 __global__ void __launch_bounds__(256)
-vq_l2_argmin_kernel(const float* __restrict__ x, const float* __restrict__ cb, int64_t* __restrict__ ids, int64_t tokens, int K, int D) {
-  extern __shared__ float xs[];                    // [VQ_TOK][D]
-  __shared__ float bd[8][VQ_TOK]; __shared__ int bi[8][VQ_TOK];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t t0 = (int64_t)blockIdx.x * VQ_TOK;
-  for (int i = threadIdx.x; i < VQ_TOK * D; i += blockDim.x) { const int64_t t = t0 + i / D; xs[i] = t < tokens ? x[t * D + (i % D)] : 0.f; }
-  __syncthreads();
-  float best[VQ_TOK]; int besti[VQ_TOK];
+vq_l2_argmin_kernel(const float* __restrict__ x, const float* __restrict__ cb, unsigned long long* __restrict__ best, int64_t tokens, int K, int D) {
+  __shared__ float Xs[16][64 + 4];
+  __shared__ float Es[16][64 + 4];
+  __shared__ float Ds[64][64 + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t t0 = (int64_t)blockIdx.x * 64;
+  const int k0 = blockIdx.y * 64;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+  float acc[4][4] = {}; float e2[4] = {};
+  for (int d0 = 0; d0 < D; d0 += 16) {
 #pragma unroll
-  for (int j = 0; j < VQ_TOK; ++j) { best[j] = FLT_MAX; besti[j] = 0x7fffffff; }
-  for (int k = warp; k < K; k += 8) {
-    const float* e = cb + (int64_t)k * D;
-    float dot[VQ_TOK]; float e2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < VQ_TOK; ++j) dot[j] = 0.f;
-    for (int c = lane; c < D; c += 32) {
-      const float ev = __ldg(e + c);
-      e2 = fmaf(ev, ev, e2);
-#pragma unroll
-      for (int j = 0; j < VQ_TOK; ++j) dot[j] = fmaf(ev, xs[j * D + c], dot[j]);
+    for (int j = 0; j < 4; ++j) {
+      const int d = d0 + lk + j;
+      Xs[lk + j][lr] = (t0 + lr < tokens && d < D) ? x[(t0 + lr) * D + d] : 0.f;
+      Es[lk + j][lr] = (k0 + lr < K && d < D) ? __ldg(cb + (int64_t)(k0 + lr) * D + d) : 0.f;
     }
-    e2 = warp_sum(e2);
+    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < VQ_TOK; ++j) {
-      const float d = e2 - 2.f * warp_sum(dot[j]);
-      if (d < best[j] || (d == best[j] && k < besti[j])) { best[j] = d; besti[j] = k; }
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = Xs[kk][ty * 4 + i]; b[i] = Es[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        e2[i] = fmaf(b[i], b[i], e2[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
     }
+    __syncthreads();
   }
-  if (lane == 0) {
 #pragma unroll
-    for (int j = 0; j < VQ_TOK; ++j) { bd[warp][j] = best[j]; bi[warp][j] = besti[j]; }
-  }
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Ds[ty * 4 + i][tx * 4 + j] = e2[j] - 2.f * acc[i][j];
   __syncthreads();
-  if (threadIdx.x < VQ_TOK) {
-    const int j = threadIdx.x; float d = bd[0][j]; int i = bi[0][j];
-    for (int w = 1; w < 8; ++w) if (bd[w][j] < d || (bd[w][j] == d && bi[w][j] < i)) { d = bd[w][j]; i = bi[w][j]; }
-    if (t0 + j < tokens) ids[t0 + j] = i;
+  if (tid < 64 && t0 + tid < tokens) {
+    unsigned long long bst = ~0ull;
+    for (int j = 0; j < 64 && k0 + j < K; ++j) {
+      const uint32_t u = __float_as_uint(Ds[tid][j]);
+      const uint32_t key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      const unsigned long long cand = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(k0 + j);
+      bst = cand < bst ? cand : bst;
+    }
+    atomicMin(best + t0 + tid, bst);
   }
 }
 
@@ -135,10 +150,15 @@ extern "C" int mmg_vq_l2_argmin(const mmg_vq_l2_argmin_args* a, void* stream) {
   MMG_CHECK_ARG(a && a->x && a->codebook && a->ids, "mmg_vq_l2_argmin: NULL pointer");
   MMG_CHECK_ARG(a->K >= 1 && a->D >= 1, "mmg_vq_l2_argmin: K, D");
   if (a->T == 0) return MMG_OK;
-  const size_t smem = (size_t)VQ_TOK * a->D * 4;
-  MMG_CHECK_ARG(smem <= 200 * 1024, "mmg_vq_l2_argmin: D too large");
-  MMG_CUDA(cudaFuncSetAttribute(vq_l2_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  vq_l2_argmin_kernel<<<(unsigned)((a->T + VQ_TOK - 1) / VQ_TOK), 256, smem, st>>>(a->x, a->codebook, a->ids, a->T, a->K, a->D);
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(a->ids);       // ids double as the packed (distance, code) keys
+  const unsigned nb = (unsigned)((a->T + 255) / 256);
+  vq_init_kernel<<<nb, 256, 0, st>>>(best, a->T);
+  MMG_LAUNCHED();
+  dim3 grid((unsigned)((a->T + 63) / 64), (unsigned)((a->K + 63) / 64));
+  MMG_CHECK_ARG(grid.y < 65536, "mmg_vq_l2_argmin: K too large");
+  vq_l2_argmin_kernel<<<grid, 256, 0, st>>>(a->x, a->codebook, best, a->T, a->K, a->D);
+  MMG_LAUNCHED();
+  vq_finish_kernel<<<nb, 256, 0, st>>>(best, a->T);
   MMG_LAUNCHED();
   return MMG_OK;
 }

@@ -4,7 +4,7 @@ import torch
 
 from . import _lib as L
 from ._lib import (F32, BF16, EPI_STORE, EPI_RESIDUAL, EPI_GEGLU, EPI_GLU, EPI_QKV, EPI_CONVT, EPI_CONVT_RGB,  # noqa: F401
-                   EPI_LNFOLD_RESIDUAL)
+                   EPI_LNFOLD_RESIDUAL, EPI_LFQ_IDS, EPI_ARGMIN)
 
 
 def _chk(t, name="tensor"):
@@ -16,7 +16,8 @@ def _epi(out=None, ldo=0, bias=None, act=0, resid=None, ldr=0, row_stats=None, l
     e = L.EpilogueArgs()
     e.row_stats = L.ptr(row_stats); e.ln_width = ln_width
     if out is not None:
-        e.out = out.data_ptr(); e.ldo = ldo; e.out_dtype = L.dt(out)
+        e.out = out.data_ptr(); e.ldo = ldo
+        e.out_dtype = L.dt(out) if out.dtype in (torch.float32, torch.bfloat16) else L.F32     # int64 outputs (LFQ ids / argmin keys)
     e.act = act
     e.bias = L.ptr(bias)
     if resid is not None:

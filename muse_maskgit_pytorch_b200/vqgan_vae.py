@@ -205,8 +205,19 @@ class VQGanVAE(nn.Module):
             lin = isinstance(q.project_in, nn.Linear)
             P["pin_w"], P["pin_b"] = (f32(q.project_in.weight), f32(q.project_in.bias)) if lin else (None, None)
             P["pout_w"], P["pout_b"] = (f32(q.project_out.weight), f32(q.project_out.bias)) if lin else (None, None)
+            P["pin_w3"] = None
+            if lin and adt == torch.bfloat16 and 3 * q.bits <= 64 and self.enc_dec.encoded_dim % 64 == 0:
+                # project_in split into three bf16 terms (hi + mid + lo reproduces the fp32 weight to 24 bits) stacked as the 64 rows of
+                # one tcgen05 GEMM; the LFQ_IDS epilogue recombines them, adds the bias, takes signs and packs the id
+                w = P["pin_w"]
+                hi = w.to(adt); r1 = w - hi.float(); mid = r1.to(adt); lo = (r1 - mid.float()).to(adt)
+                w3 = torch.zeros((64, w.shape[1]), device=dev, dtype=adt)
+                w3[:q.bits], w3[q.bits:2 * q.bits], w3[2 * q.bits:3 * q.bits] = hi, mid, lo
+                P["pin_w3"] = w3.contiguous()
         else:
             P["codebook"] = f32(q.embed)
+            P["codebook_a"] = P["codebook"].to(adt).contiguous()
+            P["code_norms"] = (P["codebook_a"].float() ** 2).sum(-1).contiguous()
         self._pack = P
         return P
 
@@ -276,9 +287,14 @@ class VQGanVAE(nn.Module):
         P = self._packed()
         ids = torch.empty((x.shape[0],), device=x.device, dtype=torch.int64)
         if self.lookup_free_quantization:
-            ops.vq_lfq_encode(x, P["pin_w"], P["pin_b"], ids, self.quantizer.bits)
+            if P["pin_w3"] is not None and x.dtype == torch.bfloat16:
+                ops.linear(x, P["pin_w3"], ids, epilogue=ops.EPI_LFQ_IDS, bias=P["pin_b"], ln_width=self.quantizer.bits)   # HBM-bound TMA stream of the fmap
+            else:
+                ops.vq_lfq_encode(x, P["pin_w"], P["pin_b"], ids, self.quantizer.bits)
         else:
-            ops.vq_l2_argmin(x.to(torch.float32).contiguous(), P["codebook"], ids)
+            ids.fill_(-1)                                   # all-ones keys for the packed (distance, code) atomicMin
+            ops.linear(x, P["codebook_a"], ids, epilogue=ops.EPI_ARGMIN, bias=P["code_norms"])
+            ids &= 0xFFFFFFFF
         return ids
 
     def _codes_nhwc(self, ids_flat):

@@ -456,3 +456,50 @@ def test_linear_geglu_lnfold_pair():
     ref = x + F.layer_norm(href, (Fu,), g3, None) @ w2.t()
     ok, msg = close(xd, ref, 3e-2, 1e-2)
     assert ok, msg
+
+
+def test_lfq_ids_gemm_epilogue_bit_exact():
+    """tcgen05 path of the LFQ lookup: 3-way bf16 split of project_in + LFQ_IDS epilogue; dyadic data -> bit-identical ids."""
+    T, D, bits = 1000, 2048, 16
+    bf = torch.bfloat16
+    x = torch.from_numpy(synth.dyadic("vx", (T, D), bits=4, span=2.0))
+    w = torch.from_numpy(synth.dyadic("vw", (bits, D), bits=4, span=1.0)) + torch.from_numpy(synth.dyadic("vw2", (bits, D), bits=4, span=1.0)) * 2.0 ** -12
+    bias = torch.from_numpy(synth.dyadic("vb", (bits,), bits=4, span=1.0))
+    hi = w.to(bf); r1 = w - hi.float(); mid = r1.to(bf); lo = (r1 - mid.float()).to(bf)
+    assert torch.equal(hi.float() + mid.float() + lo.float(), w)
+    w3 = torch.zeros((64, D), dtype=bf); w3[:bits], w3[bits:2 * bits], w3[2 * bits:3 * bits] = hi, mid, lo
+    ids = torch.empty((T,), dtype=torch.int64, device="cuda")
+    ops().linear(dev(x, bf), dev(w3), ids, epilogue=ops().EPI_LFQ_IDS, bias=dev(bias), ln_width=bits)
+    proj = x.double() @ w.double().t() + bias.double()
+    ref = ((proj > 0).long() * (2 ** torch.arange(bits - 1, -1, -1))).sum(-1)
+    assert torch.equal(ids.cpu(), ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+def test_argmin_gemm_epilogue(dtype):
+    T, K, D = 200, 1024, 128
+    x = torch.from_numpy(synth.dyadic("ax", (T, D), bits=3, span=2.0))
+    cb = torch.from_numpy(synth.dyadic("acb", (K, D), bits=3, span=2.0))
+    cb[700] = cb[33]
+    best = torch.full((T,), -1, dtype=torch.int64, device="cuda")
+    norms = (cb * cb).sum(-1)
+    ops().linear(dev(x, dtype), dev(cb, dtype), best, epilogue=ops().EPI_ARGMIN, bias=dev(norms))
+    assert torch.equal((best & 0xFFFFFFFF).cpu(), O.vq_l2_argmin(x, cb))
+
+
+def test_logits_sample_philox_matches_oracle_stream():
+    """In-kernel Philox4x32-10 draws exactly the uniforms oracle/philox.py produces for (seed, step, global row, v): the
+    sampled ids equal the oracle's on that stream wherever the perturbed top-2 margin exceeds the fast-log error."""
+    from oracle import philox
+    b, n, nm, V, seed, step, off = 2, 16, 6, 8192, 987654321012, 5, 3 * 16
+    k = O.top_k_count(V, 0.9)
+    logits = torch.from_numpy(synth.normal("lgq", (b, nm, V), 13, 0.58))
+    g = torch.Generator().manual_seed(4)
+    mp = torch.stack([torch.sort(torch.randperm(n, generator=g)[:nm]).values for _ in range(b)]).int()
+    ids = torch.full((b, n), V, dtype=torch.long, device="cuda"); sc = torch.full((b, n), -1e5, device="cuda")
+    ops().logits_sample(dev(logits.reshape(-1, V).contiguous()), dev(mp), ids, sc, nm, k, 0.7, seed=seed, step=step, row_offset=off)
+    rows_u = torch.stack([torch.from_numpy(philox.uniform(seed, step, off + bi * n + int(mp[bi, j]), V)) for bi in range(b) for j in range(nm)])
+    pred, score, margin = _oracle_rows(logits.reshape(-1, V), rows_u, 0.7, k)
+    got = torch.stack([ids.cpu()[bi, mp[bi, j]] for bi in range(b) for j in range(nm)])
+    assert torch.equal(got[margin > 1e-3], pred[margin > 1e-3]), (got.tolist(), pred.tolist())
+    assert (got == pred).float().mean() > 0.9

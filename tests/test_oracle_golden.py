@@ -97,3 +97,13 @@ def test_generate_superres_small():
     images, ids = O.generate(sd, CFG, vsd, 10, te, 8, util.torch_noise_fn(778), cond_images=cond, timesteps=8)
     assert torch.equal(ids.view(2, 8, 8), g["ids"])
     assert torch.allclose(images, g["images"], atol=1e-5)
+
+
+def test_philox_known_answer():
+    """Random123 known-answer vector for Philox4x32-10 (zero counter, zero key -> 6627e8d5 ...): pins oracle/philox.py,
+    against which the in-kernel generator is tested on the GPU."""
+    from oracle import philox
+    u = philox.uniform(0, 0, 0, 1)
+    assert int(round(float(u[0]) * (1 << 24))) == 0x6627e8d5 >> 8
+    a, b = philox.uniform(5, 1, 2, 64), philox.uniform(5, 1, 3, 64)
+    assert not np.array_equal(a, b) and a.min() >= 0 and a.max() < 1
