@@ -174,6 +174,17 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
             }
           } else {
             uint32_t packed[16];
+            if (!km && j0 + 32 <= p.Tk) {
+              // fast path (self-attention, chunk fully inside the key range): no per-key liveness tests
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float p0 = exp2f(fmaf(s[i], p.scale_log2e, -mneg)), p1 = exp2f(fmaf(s[i + 1], p.scale_log2e, -mneg));
+                __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+                packed[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+                const float2 pr = __bfloat1622float2(t);
+                row_sum += pr.x + pr.y;
+              }
+            } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               float pv[2];
@@ -187,6 +198,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
               packed[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
               const float2 pr = __bfloat1622float2(t);     // normalise by the sum of the ROUNDED weights: O = sum(p~ v) / sum(p~)
               row_sum += pr.x + pr.y;
+            }
             }
             // P[r, c .. c+31] -> sub-tile (c / 64), 16-byte chunks (c % 64) / 8 .. +3, 128B swizzle: chunk ^= (r & 7)
             uint8_t* tile = sP + (c >> 6) * 16384 + r * 128;
