@@ -67,6 +67,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   extern __shared__ uint8_t smraw[];
   float* lval = reinterpret_cast<float*>(smraw);                 // [SMP_CAP] candidate logits
   int* lidx = reinterpret_cast<int*>(lval + SMP_CAP);            // [SMP_CAP] candidate vocabulary indices
+  float4* scr = reinterpret_cast<float4*>(lidx + SMP_CAP);       // [4][SMP_THREADS] per-thread staging of the 16 values in flight
   __shared__ int s_count, s_n;
   __shared__ int s_red[64];
   __shared__ float s_redf[32]; __shared__ int s_redi[32]; __shared__ int s_redj[32];
@@ -118,7 +119,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
     // sampled rows: every warp finds the rank-(rs/16) key of ITS 256 samples with shuffles only (no block barrier), the block
     // threshold is the mean of the 16 warp estimates (same variance as one 4096-sample quantile; exactness is restored below)
     const float pf = (float)k / (float)V; const float mu = pf * ns;
-    const int rs = (int)(mu + 4.5f * sqrtf(mu * (1.f - pf)) + 2.f);
+    const int rs = (int)(mu + 4.0f * sqrtf(mu * (1.f - pf)) + 2.f);
     const int rw = (rs + SMP_THREADS / 32 - 1) / (SMP_THREADS / 32);
     uint32_t prefix = 0;
     for (int bit = 30; bit >= 12; bit -= 2) {                          // 20 key bits are plenty for a lower bound
@@ -187,9 +188,13 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
           for (int u = 0; u < UNR; ++u) if (i0 + u * SMP_THREADS + tid < n4) mask |= 0xFu << (4 * u);
         }
       }
-      // warp-aggregated append of the candidate INDICES (one shared-memory atomic per warp per 16 elements per thread);
-      // the values are re-read from the (L2-resident) row when the list is consumed
+      // warp-aggregated append (one shared-memory atomic per warp per 16 elements per thread); the values pass through a
+      // per-thread shared-memory staging row so the set bits can be walked without dynamic register indexing
       const int c = __popc(mask);
+      if (mask) {
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) scr[u * SMP_THREADS + tid] = make_float4(xs[4 * u], xs[4 * u + 1], xs[4 * u + 2], xs[4 * u + 3]);
+      }
       int incl = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -200,7 +205,10 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
         start = __shfl_sync(0xffffffffu, start, 0) + incl - c;
         while (mask) {
           const int j = __ffs(mask) - 1; mask &= mask - 1;
-          if (start < SMP_CAP) lidx[start] = (i0 + (j >> 2) * SMP_THREADS + tid) * 4 + (j & 3);
+          if (start < SMP_CAP) {
+            lidx[start] = (i0 + (j >> 2) * SMP_THREADS + tid) * 4 + (j & 3);
+            lval[start] = reinterpret_cast<const float*>(scr + (j >> 2) * SMP_THREADS + tid)[j & 3];
+          }
           ++start;
         }
       }
@@ -223,7 +231,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
         int start = 0;
         if (lane == 0) start = atomicAdd(&s_count, tot);
         start = __shfl_sync(0xffffffffu, start, 0) + incl - c;
-        if (c && start < SMP_CAP) lidx[start] = i;
+        if (c && start < SMP_CAP) { lidx[start] = i; lval[start] = x; }
       }
     }
   }
@@ -244,10 +252,6 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
     __syncthreads();
   }
   int n = s_n;
-  if (n >= k && n <= SMP_CAP) {                        // candidate values: gather from the row just streamed (L2 hits)
-    for (int sl = tid; sl < n; sl += SMP_THREADS) lval[sl] = row[lidx[sl]];
-    __syncthreads();
-  }
 
   // ---------------- rare: exact rebuild when the sample threshold missed ----------------
   if (n < k || n > SMP_CAP) {
@@ -406,7 +410,7 @@ extern "C" int mmg_logits_sample(const mmg_logits_sample_args* a, void* stream) 
   MMG_CHECK_ARG(a->k >= 1 && a->k <= a->V && a->k <= SMP_CAP, "mmg_logits_sample: k=%d out of range (<= %d)", a->k, SMP_CAP);
   const int64_t R = (int64_t)a->B * a->num_masked;
   if (R == 0) return MMG_OK;
-  static const size_t smem = (size_t)SMP_CAP * 8;
+  static const size_t smem = (size_t)SMP_CAP * 8 + (size_t)SMP_THREADS * 64;
   static cudaError_t attr0 = cudaFuncSetAttribute(logits_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   static cudaError_t attr1 = cudaFuncSetAttribute(logits_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (attr0 != cudaSuccess || attr1 != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(logits_sample): %s", cudaGetErrorString(attr0 != cudaSuccess ? attr0 : attr1));
