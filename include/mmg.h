@@ -154,6 +154,7 @@ typedef struct {
   const float* add;        /* [width] or NULL                                                                    */
   float*       x_out;      /* fp32 [rows, ldx] or NULL                                                           */
   float*       zero_stats; /* optional [rows, 2]: reset to 0 (row statistics accumulated by a later GEGLU epilogue)     */
+  int64_t      add_from;   /* `add` / `x_out` apply to rows >= add_from only (null-CFG branch rows of a 2-branch batch)   */
   int64_t rows, width, ldx, ldy;
 } mmg_layernorm_args;
 int mmg_layernorm(const mmg_layernorm_args* a, void* stream);

@@ -49,7 +49,7 @@ class GroupNormArgs(C.Structure):
 
 
 class LayerNormArgs(C.Structure):
-    _fields_ = [("x", vp), ("x_dtype", i32), ("y_dtype", i32), ("y", vp), ("gamma", vp), ("add", vp), ("x_out", vp), ("zero_stats", vp),
+    _fields_ = [("x", vp), ("x_dtype", i32), ("y_dtype", i32), ("y", vp), ("gamma", vp), ("add", vp), ("x_out", vp), ("zero_stats", vp), ("add_from", i64),
                 ("rows", i64), ("width", i64), ("ldx", i64), ("ldy", i64)]
 
 

@@ -80,7 +80,7 @@ static int attn_launch_cols(const AttnTcParams& p, dim3 grid, size_t smem, cudaS
   static std::once_flag once; static cudaError_t err = cudaSuccess;
   std::call_once(once, [] { err = cudaFuncSetAttribute(attention_tc_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
   if (err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(attention_tc): %s", cudaGetErrorString(err));
-  attention_tc_kernel<COLS><<<grid, 160, smem, st>>>(p);
+  MMG_CUDA(launch_pdl(attention_tc_kernel<COLS>, grid, dim3(160), smem, st, p));
   MMG_LAUNCHED();
   return MMG_OK;
 }

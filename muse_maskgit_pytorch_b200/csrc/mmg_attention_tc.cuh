@@ -61,6 +61,8 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tS = tmem_base;                       // KB fp32 columns
   const uint32_t tO = tmem_base + TMEM_COLS - 64;      // 64 fp32 columns
 

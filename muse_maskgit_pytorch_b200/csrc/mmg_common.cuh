@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <atomic>
+#include <stdlib.h>
+#include <utility>
 #include "../../include/mmg.h"
 
 namespace mmg {
@@ -32,6 +34,24 @@ inline int num_sms() {
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
   return n;
 }
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// Hot-loop kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs become
+// resident (and run their prologue) while the previous grid drains, then block in griddepcontrol.wait until that grid has
+// completed and flushed.  Every kernel launched this way calls pdl_wait() before its first global access.  MMG_PDL=0 disables.
+inline bool pdl_enabled() { static int v = -1; if (v < 0) { const char* e = getenv("MMG_PDL"); v = (e && e[0] == '0') ? 0 : 1; } return v != 0; }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- device helpers --------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f(T v);

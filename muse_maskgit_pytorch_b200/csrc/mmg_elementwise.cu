@@ -12,11 +12,12 @@ constexpr int LN_MAXV = 16;   // float4 chunks per lane -> width <= 2048
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ add,
-                 float* __restrict__ x_out, float* __restrict__ zero_stats, int64_t rows, int width, int64_t ldx, int64_t ldy) {
+                 float* __restrict__ x_out, float* __restrict__ zero_stats, int64_t add_from, int64_t rows, int width, int64_t ldx, int64_t ldy) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   if (zero_stats && lane == 0) *reinterpret_cast<float2*>(zero_stats + 2 * row) = make_float2(0.f, 0.f);
+  if (row < add_from) { add = nullptr; x_out = nullptr; }
   const TX* xr = x + row * ldx;
   float v[LN_MAXV * 4];
   float sum = 0.f;
@@ -94,12 +95,14 @@ template <> __device__ __forceinline__ void store_vec<bf16, 4>(bf16* p, const fl
 template <typename TX, typename TY, int CH>
 __global__ void __launch_bounds__(256)
 layernorm_vec_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ add,
-                     float* __restrict__ x_out, float* __restrict__ zero_stats, int64_t rows, int width, int64_t ldx, int64_t ldy) {
+                     float* __restrict__ x_out, float* __restrict__ zero_stats, int64_t add_from, int64_t rows, int width, int64_t ldx, int64_t ldy) {
   constexpr int VN = VecIO<TX>::N;
+  pdl_wait(); pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   if (zero_stats && lane == 0) *reinterpret_cast<float2*>(zero_stats + 2 * row) = make_float2(0.f, 0.f);
+  if (row < add_from) { add = nullptr; x_out = nullptr; }
   const TX* xr = x + row * ldx;
   float v[CH][VN];
   float sum = 0.f;
@@ -148,6 +151,7 @@ layernorm_vec_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* 
 // x[copy][r, :] = token_emb[ids[r]] + pos_emb[r % n]        ref: muse_maskgit_pytorch.py:322-323 (and 316 with use_pos = 0)
 __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
                              float* __restrict__ x, int64_t rows, int64_t n, int64_t dim, int copies, int use_pos) {
+  pdl_wait(); pdl_trigger();
   const int64_t row = blockIdx.x;
   const int64_t id = ids[row];
   const float4* t = reinterpret_cast<const float4*>(tok + id * dim);
@@ -164,6 +168,7 @@ template <typename TE>
 __global__ void __launch_bounds__(256)
 final_embed_kernel(const float* __restrict__ xc, const float* __restrict__ xn, const float* __restrict__ gamma,
                    const int32_t* __restrict__ masked_pos, TE* __restrict__ e, int B, int n, int num_masked, int dim, float s) {
+  pdl_wait(); pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t j = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (j >= (int64_t)B * num_masked) return;
@@ -315,10 +320,10 @@ extern "C" int mmg_layernorm(const mmg_layernorm_args* a, void* stream) {
   const bool vec = (a->ldx % vn == 0) && (a->ldy % vn == 0) && ((reinterpret_cast<uintptr_t>(a->x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a->y) & 15) == 0) &&
                    (!a->add || (w % vn == 0 && (reinterpret_cast<uintptr_t>(a->add) & 15) == 0)) && (!a->x_out || w % vn == 0) &&
                    ((w + vn - 1) / vn * vn <= a->ldx) && span <= 16 * 32 * vn;
-#define LNV(TX, TY, CH) layernorm_vec_kernel<TX, TY, CH><<<grid, 256, 0, st>>>((const TX*)a->x, (TY*)a->y, a->gamma, a->add, a->x_out, a->zero_stats, a->rows, w, a->ldx, a->ldy)
+#define LNV(TX, TY, CH) launch_pdl(layernorm_vec_kernel<TX, TY, CH>, dim3(grid), dim3(256), 0, st, (const TX*)a->x, (TY*)a->y, a->gamma, a->add, a->x_out, a->zero_stats, a->add_from, a->rows, w, a->ldx, a->ldy)
 #define LNV_DISPATCH(TX, TY) do { const int64_t per = 32 * vn; const int ch = (int)((span + per - 1) / per); \
     if (ch <= 4) LNV(TX, TY, 4); else if (ch <= 6) LNV(TX, TY, 6); else if (ch <= 8) LNV(TX, TY, 8); else LNV(TX, TY, 16); } while (0)
-#define LN_LAUNCH(TX, TY) layernorm_kernel<TX, TY><<<grid, 256, 0, st>>>((const TX*)a->x, (TY*)a->y, a->gamma, a->add, a->x_out, a->zero_stats, a->rows, w, a->ldx, a->ldy)
+#define LN_LAUNCH(TX, TY) layernorm_kernel<TX, TY><<<grid, 256, 0, st>>>((const TX*)a->x, (TY*)a->y, a->gamma, a->add, a->x_out, a->zero_stats, a->add_from, a->rows, w, a->ldx, a->ldy)
   if (a->x_dtype == MMG_F32 && a->y_dtype == MMG_F32) { if (vec) LNV_DISPATCH(float, float); else LN_LAUNCH(float, float); }
   else if (a->x_dtype == MMG_F32 && a->y_dtype == MMG_BF16) { if (vec) LNV_DISPATCH(float, bf16); else LN_LAUNCH(float, bf16); }
   else if (a->x_dtype == MMG_BF16 && a->y_dtype == MMG_BF16) { if (vec) LNV_DISPATCH(bf16, bf16); else LN_LAUNCH(bf16, bf16); }
@@ -335,7 +340,7 @@ extern "C" int mmg_embed(const mmg_embed_args* a, void* stream) {
   MMG_CHECK_ARG(a && a->ids && a->token_emb && a->x && (a->pos_emb || !a->use_pos), "mmg_embed: NULL pointer");
   MMG_CHECK_ARG(a->dim % 4 == 0 && a->copies >= 1 && a->n > 0, "mmg_embed: dim %% 4, copies, n");
   if (a->rows == 0) return MMG_OK;
-  embed_kernel<<<(unsigned)a->rows, 128, 0, st>>>(a->ids, a->token_emb, a->use_pos ? a->pos_emb : a->token_emb, a->x, a->rows, a->n, a->dim, a->copies, a->use_pos);
+  MMG_CUDA(launch_pdl(embed_kernel, dim3((unsigned)a->rows), dim3(128), 0, st, a->ids, a->token_emb, a->use_pos ? a->pos_emb : a->token_emb, a->x, a->rows, a->n, a->dim, a->copies, a->use_pos));
   MMG_LAUNCHED();
   return MMG_OK;
 }
@@ -347,8 +352,8 @@ extern "C" int mmg_final_embed(const mmg_final_embed_args* a, void* stream) {
   const int64_t R = (int64_t)a->B * a->num_masked;
   if (R == 0) return MMG_OK;
   const unsigned grid = (unsigned)((R + 7) / 8);
-  if (a->e_dtype == MMG_BF16) final_embed_kernel<bf16><<<grid, 256, 0, st>>>(a->x_cond, a->x_null, a->gamma, a->masked_pos, (bf16*)a->e, a->B, a->n, a->num_masked, a->dim, a->cond_scale);
-  else final_embed_kernel<float><<<grid, 256, 0, st>>>(a->x_cond, a->x_null, a->gamma, a->masked_pos, (float*)a->e, a->B, a->n, a->num_masked, a->dim, a->cond_scale);
+  if (a->e_dtype == MMG_BF16) MMG_CUDA(launch_pdl(final_embed_kernel<bf16>, dim3(grid), dim3(256), 0, st, a->x_cond, a->x_null, a->gamma, a->masked_pos, (bf16*)a->e, a->B, a->n, a->num_masked, a->dim, a->cond_scale));
+  else MMG_CUDA(launch_pdl(final_embed_kernel<float>, dim3(grid), dim3(256), 0, st, a->x_cond, a->x_null, a->gamma, a->masked_pos, (float*)a->e, a->B, a->n, a->num_masked, a->dim, a->cond_scale));
   MMG_LAUNCHED();
   return MMG_OK;
 }

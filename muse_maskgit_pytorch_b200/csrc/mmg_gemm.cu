@@ -13,7 +13,7 @@ static int launch_tc(const TcGemmParams& p, cudaStream_t st) {
   if (attr_err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(tc_gemm<%d>): %s", BN, cudaGetErrorString(attr_err));
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  tc_gemm_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(p);
+  MMG_CUDA(launch_pdl(tc_gemm_kernel<BN>, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES, st, p));
   MMG_LAUNCHED();
   return MMG_OK;
 }

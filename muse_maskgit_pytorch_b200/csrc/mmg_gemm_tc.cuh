@@ -81,6 +81,8 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                                   // everything above overlapped the previous kernel's tail
+  pdl_trigger();
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");

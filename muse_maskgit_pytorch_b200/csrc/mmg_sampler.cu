@@ -73,6 +73,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   __shared__ float s_redf[32]; __shared__ int s_redi[32]; __shared__ int s_redj[32];
   __shared__ float s_max, s_sum;
 
+  pdl_wait(); pdl_trigger();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = a.V, k = a.k;
   const int64_t r = blockIdx.x;
@@ -370,6 +371,7 @@ remask_kernel(int64_t* __restrict__ ids, float* __restrict__ scores, int32_t* __
   extern __shared__ float sc[];                       // [n] scores, then [n] flags (as int)
   int* flag = reinterpret_cast<int*>(sc + n);
   __shared__ int woff[9];
+  pdl_wait(); pdl_trigger();
   const int b = blockIdx.x, tid = threadIdx.x;
   for (int i = tid; i < n; i += 256) sc[i] = scores[(int64_t)b * n + i];
   __syncthreads();
@@ -415,8 +417,8 @@ extern "C" int mmg_logits_sample(const mmg_logits_sample_args* a, void* stream) 
   static cudaError_t attr1 = cudaFuncSetAttribute(logits_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (attr0 != cudaSuccess || attr1 != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(logits_sample): %s", cudaGetErrorString(attr0 != cudaSuccess ? attr0 : attr1));
   float t = a->temperature; if (t < 1e-10f) t = 1e-10f;      // max(temperature, 1e-10): muse_maskgit_pytorch.py:411
-  if (a->u) logits_sample_kernel<true><<<(unsigned)R, SMP_THREADS, smem, st>>>(*a, t);
-  else logits_sample_kernel<false><<<(unsigned)R, SMP_THREADS, smem, st>>>(*a, t);
+  if (a->u) MMG_CUDA(launch_pdl(logits_sample_kernel<true>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, *a, t));
+  else MMG_CUDA(launch_pdl(logits_sample_kernel<false>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, *a, t));
   MMG_LAUNCHED();
   return MMG_OK;
 }
@@ -426,7 +428,7 @@ extern "C" int mmg_remask(const mmg_remask_args* a, void* stream) {
   MMG_CHECK_ARG(a && a->ids && a->scores && a->masked_pos, "mmg_remask: NULL pointer");
   MMG_CHECK_ARG(a->n > 0 && a->num_masked >= 1 && a->num_masked <= a->n && a->n <= 16384, "mmg_remask: n=%d num_masked=%d", a->n, a->num_masked);
   if (a->B == 0) return MMG_OK;
-  remask_kernel<<<a->B, 256, (size_t)a->n * 8, st>>>(a->ids, a->scores, a->masked_pos, a->n, a->num_masked, a->mask_id);
+  MMG_CUDA(launch_pdl(remask_kernel, dim3(a->B), dim3(256), (size_t)a->n * 8, st, a->ids, a->scores, a->masked_pos, a->n, a->num_masked, a->mask_id));
   MMG_LAUNCHED();
   return MMG_OK;
 }

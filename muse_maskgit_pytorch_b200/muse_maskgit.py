@@ -264,13 +264,19 @@ class Transformer(nn.Module):
                               ctx["m"] + 1, key_mask=ctx["key_mask"][:len(live) * b], logit_bound=ca["bound"])
                 ops.linear(ao[:Rl], ca["wo"], x[:Rl], epilogue=ops.EPI_RESIDUAL, resid=x[:Rl])
             # --- feed forward (the constant null-branch cross-attention term is folded into this LayerNorm) ---
-            for j in range(nb):
-                xs = x[j * bn:(j + 1) * bn]
-                zs = ws["stats"][j * bn:(j + 1) * bn]          # row statistics of the GEGLU output, reset here, accumulated by FF1's epilogue
-                if j in pending_add:
-                    ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn], add=pending_add[j], x_out=xs, zero_stats=zs)
-                else:
-                    ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn], zero_stats=zs)
+            if pending_add and sorted(pending_add) == list(range(min(pending_add), nb)):
+                # one launch for all branches: rows of the all-masked (null) branches get += to_out(null_v) before the norm
+                ops.layernorm(x, ff["g0"], xn, add=ca["null_out"], x_out=x, zero_stats=ws["stats"], add_from=min(pending_add) * bn)
+            elif not pending_add:
+                ops.layernorm(x, ff["g0"], xn, zero_stats=ws["stats"])
+            else:
+                for j in range(nb):
+                    xs = x[j * bn:(j + 1) * bn]
+                    zs = ws["stats"][j * bn:(j + 1) * bn]      # row statistics of the GEGLU output, reset here, accumulated by FF1's epilogue
+                    if j in pending_add:
+                        ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn], add=pending_add[j], x_out=xs, zero_stats=zs)
+                    else:
+                        ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn], zero_stats=zs)
             self._ff_tail(xn, ff, x, ws, R)
         return x
 

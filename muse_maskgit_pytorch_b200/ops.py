@@ -104,9 +104,9 @@ def groupnorm_(x, gamma, beta, B, HW, Cch, groups=16, act=0):
     return x
 
 
-def layernorm(x, gamma, y, width=None, add=None, x_out=None, rows=None, zero_stats=None):
+def layernorm(x, gamma, y, width=None, add=None, x_out=None, rows=None, zero_stats=None, add_from=0):
     a = L.LayerNormArgs()
-    a.zero_stats = L.ptr(zero_stats)
+    a.zero_stats = L.ptr(zero_stats); a.add_from = add_from
     a.x = _chk(x).data_ptr(); a.x_dtype = L.dt(x); a.y = _chk(y).data_ptr(); a.y_dtype = L.dt(y)
     a.gamma = gamma.data_ptr(); a.add = L.ptr(add); a.x_out = L.ptr(x_out)
     a.rows = x.shape[0] if rows is None else rows
