@@ -316,7 +316,9 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH, help="experiments only; the benchmark config is 64")
     args = ap.parse_args()
+    GLOBAL_BATCH = args.global_batch
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -82,6 +82,12 @@ typedef struct {
   int32_t      heads, tokens, q_rows, kv_rows, key_off, nq_heads, nk_heads, nv_heads;
   /* CONVT(_RGB): input geometry of the GEMM rows (b, y, x) and the output parity                                  */
   int32_t      H, W, py, px;
+  /* Fused LayerNorm of the OUTPUT row (RESIDUAL / LNFOLD_RESIDUAL with N == 2 tile widths, bf16 tensor-core path): besides
+   * out = epilogue(acc) + resid the kernel also writes ln_out[r, :] = LN(out[r, :]) * gamma as bf16 for the next matrix product.
+   * Rows >= ln_split first get out += ln_add[:] and use ln_gamma_b (null-CFG rows whose cross-attention is the constant
+   * to_out(null_v)).  The two CTAs that own the halves of a row exchange (sum, sumsq) through distributed shared memory.  */
+  void*        ln_out; int64_t ld_ln;
+  const float* ln_gamma; const float* ln_gamma_b; const float* ln_add; int64_t ln_split;
   float*       row_stats;  /* [M, 2] fp32 (sum, sum of squares). GEGLU: the epilogue atomically ACCUMULATES its fp32 outputs;
                               LNFOLD_RESIDUAL: read (statistics over ln_width columns, eps 1e-5)                       */
   int32_t      ln_width; int32_t _pad0;

@@ -18,6 +18,25 @@ static int launch_tc(const TcGemmParams& p, cudaStream_t st) {
   return MMG_OK;
 }
 
+// LayerNorm-fused variant: clusters of two CTAs (column halves of the same rows), grid = 2 * min(#m-tiles, #SM / 2)
+template <int BN>
+static int launch_tc_lnf(const TcGemmParams& p, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES); });
+  if (attr_err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(tc_gemm_lnf<%d>): %s", BN, cudaGetErrorString(attr_err));
+  const int pairs = p.num_m_tiles < num_sms() / 2 ? p.num_m_tiles : num_sms() / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<BN>::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  MMG_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, true>, p));
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
 static int pick_bn(int64_t M_tiles, int64_t N, int epilogue) {
   if (epilogue == MMG_EPI_CONVT_RGB) return (int)N;             // whole row in one tile
   if (N % 256 == 0 && M_tiles * (N / 256) >= 2 * 148) return 256;
@@ -163,6 +182,7 @@ extern "C" int mmg_linear(const mmg_linear_args* a, void* stream) {
   const bool tc_ok = a->dtype == MMG_BF16 && (a->K % 64 == 0) && (a->N % 64 == 0) && (a->lda % 8 == 0) && (a->ldw % 8 == 0) &&
                      aligned16(a->a) && aligned16(a->w) && (a->epi.ldo % 8 == 0 || a->epilogue == MMG_EPI_QKV || a->epilogue == MMG_EPI_CONVT_RGB || a->epilogue == MMG_EPI_LFQ_IDS || a->epilogue == MMG_EPI_ARGMIN);
   if (!tc_ok) {
+    MMG_CHECK_ARG(!a->epi.ln_out, "fused LayerNorm output requires the bf16 tensor-core path (K %% 64, N %% 64, aligned operands)");
     ConvGeom g{};
     return launch_simt<false>(a->dtype, a->a, a->w, a->M, a->N, a->K, a->lda, a->ldw, g, epi, st);
   }
@@ -172,6 +192,17 @@ extern "C" int mmg_linear(const mmg_linear_args* a, void* stream) {
   p.epi = epi; p.epi.fast = 1;
   uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M}; uint64_t str[1] = {(uint64_t)a->lda * 2}; uint32_t box[2] = {TC_BK, TC_BM};
   rc = make_tmap_bf16(&p.tma_a[0], a->a, 2, dims, str, box); if (rc) return rc;
+  if (a->epi.ln_out) {
+    const int bn = (int)(a->N / 2);
+    MMG_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "fused LayerNorm output needs N in {128, 256, 512} (two column tiles), got %lld", (long long)a->N);
+    MMG_CHECK_ARG((a->epilogue == MMG_EPI_RESIDUAL && a->epi.out_dtype == MMG_F32 && a->epi.act == 0 && a->epi.ldr % 8 == 0) || a->epilogue == MMG_EPI_LNFOLD_RESIDUAL,
+                  "fused LayerNorm output is offered for the fp32 RESIDUAL / LNFOLD_RESIDUAL epilogues");
+    MMG_CHECK_ARG(a->epi.ln_gamma && a->epi.ld_ln % 8 == 0, "fused LayerNorm output: gamma / ld_ln");
+    uint64_t dimsb[2] = {(uint64_t)a->K, (uint64_t)a->N}; uint64_t strb[1] = {(uint64_t)a->ldw * 2}; uint32_t boxb[2] = {TC_BK, (uint32_t)bn};
+    rc = make_tmap_bf16(&p.tma_b, a->w, 2, dimsb, strb, boxb); if (rc) return rc;
+    p.num_n_tiles = 2;
+    switch (bn) { case 64: return launch_tc_lnf<64>(p, st); case 128: return launch_tc_lnf<128>(p, st); default: return launch_tc_lnf<256>(p, st); }
+  }
   const int bn = pick_bn(p.num_m_tiles, a->N, a->epilogue);
   MMG_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "mmg_linear: unsupported N=%lld for this epilogue", (long long)a->N);
   return dispatch_tc(p, bn, a->w, a->N, a->K, a->ldw, st);

@@ -46,7 +46,9 @@ template <int BN> struct TcCfg {
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
-template <int BN>
+// LNF: the epilogue additionally emits LayerNorm(out row) as bf16 (see mmg_epilogue_args::ln_out).  Launched as clusters of two
+// CTAs that own the two column halves (N == 2 * BN) of the same 128 rows; per-row (sum, sumsq) partials cross through DSMEM.
+template <int BN, bool LNF = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   using namespace sm100;
@@ -62,7 +64,12 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = LNF ? p.num_m_tiles : p.num_m_tiles * p.num_n_tiles;      // LNF: this CTA walks m-blocks, n-block = cluster rank
+  const int tile0 = LNF ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = LNF ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int my_rank = LNF ? (int)(blockIdx.x & 1) : 0;
+  __shared__ float s_part[LNF ? 2 : 1][2][LNF ? 128 : 1][2][2];                    // [buffer][cta rank][row][column half][sum, sumsq]
+  __shared__ uint64_t s_bar_stats;
   __shared__ float s_scale[128];               // QKV epilogue: q_scale | k_scale staged once per CTA
   if (p.epi.kind == MMG_EPI_QKV && threadIdx.x < 128) {
     const float* src = threadIdx.x < 64 ? p.epi.p.q_scale : p.epi.p.k_scale;
@@ -74,6 +81,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     prefetch_tmap(&p.tma_a[0]);
     for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, TC_EPI_WARPS); }
+    if (LNF) mbar_init(&s_bar_stats, 2 * TC_EPI_WARPS * 32);      // every epilogue thread of both CTAs arrives once per tile
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
@@ -81,6 +89,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (LNF) cluster_sync_all();                  // the peer's barrier must exist before the first remote arrive
   pdl_wait();                                   // everything above overlapped the previous kernel's tail
   pdl_trigger();
 
@@ -90,8 +99,8 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m_tiles, n_blk = tile / p.num_m_tiles;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_blk = LNF ? tile : tile % p.num_m_tiles, n_blk = LNF ? my_rank : tile / p.num_m_tiles;
         int x0 = 0, y0 = 0, b0 = 0;
         if (p.mode == 1) {
           const int xt = m_blk % p.tiles_x, yt = (m_blk / p.tiles_x) % p.tiles_y, bt = m_blk / (p.tiles_x * p.tiles_y);
@@ -118,7 +127,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     constexpr uint32_t idesc = idesc_bf16_f32(TC_BM, BN, false, false);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       mbar_wait(tmem_empty + acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -152,8 +161,9 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     const bool whole_row = (epi.kind == MMG_EPI_CONVT_RGB);      // needs every chunk of a row in one thread
     const bool prefetch_resid = epi.can_prefetch_resid();
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.num_m_tiles, n_blk = tile / p.num_m_tiles;
+    uint32_t stats_phase = 0; int stats_buf = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m_blk = LNF ? tile : tile % p.num_m_tiles, n_blk = LNF ? my_rank : tile / p.num_m_tiles;
       int64_t row; bool valid;
       if (p.mode == 0) {
         row = (int64_t)m_blk * TC_BM + r_in_tile; valid = row < p.M;
@@ -168,6 +178,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       const int c_first = whole_row ? 0 : half, c_step = whole_row ? 1 : 2;
       const bool pre = prefetch_resid && valid && mine && (n_blk * BN + c_first * 64 < p.N) && c_first < BN / 64;
       float rbuf[64];
+      float ln_sum = 0.f, ln_sq = 0.f;
       if (pre) epi.load_resid(row, n_blk * BN + c_first * 64, rbuf);      // in flight while the MMA of this tile completes
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
@@ -186,6 +197,14 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
             epi.fuse_resid(col0, v, rbuf);
             const int cn = col0 + c_step * 64;
             if (c + c_step < BN / 64 && cn < p.N) epi.load_resid(row, cn, rbuf);   // next chunk's residual overlaps the stores
+            if (LNF) {
+              if (row >= epi.p.ln_split && epi.p.ln_add) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) v[i] += __ldg(epi.p.ln_add + col0 + i);
+              }
+#pragma unroll
+              for (int i = 0; i < 64; ++i) { ln_sum += v[i]; ln_sq = fmaf(v[i], v[i], ln_sq); }
+            }
             epi.store_f32(row, col0, v);
           } else {
             epi.template apply<true>(row, col0, v, 64);
@@ -197,11 +216,46 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (LNF) {
+        // ---- LayerNorm of the freshly written row: exchange (sum, sumsq) partials with the CTA that owns the other column half ----
+        const uint32_t slot = smem_u32(&s_part[stats_buf][my_rank][r_in_tile][half][0]);
+        st_cluster_v2f32(mapa_shared(slot, my_rank), ln_sum, ln_sq);
+        st_cluster_v2f32(mapa_shared(slot, my_rank ^ 1), ln_sum, ln_sq);
+        const uint32_t bar = smem_u32(&s_bar_stats);
+        mbar_arrive_cluster(mapa_shared(bar, my_rank));
+        mbar_arrive_cluster(mapa_shared(bar, my_rank ^ 1));
+        mbar_wait_cluster(&s_bar_stats, stats_phase);
+        stats_phase ^= 1;
+        float ts = 0.f, tq = 0.f;
+#pragma unroll
+        for (int rk = 0; rk < 2; ++rk)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) { ts += s_part[stats_buf][rk][r_in_tile][hf][0]; tq += s_part[stats_buf][rk][r_in_tile][hf][1]; }
+        stats_buf ^= 1;
+        if (valid && my_rank == 0 && half == 0 && epi.kind == MMG_EPI_RESIDUAL && epi.p.row_stats)      // reset the statistics the next GEGLU epilogue accumulates
+          *reinterpret_cast<float2*>(epi.p.row_stats + 2 * row) = make_float2(0.f, 0.f);
+        if (valid) {
+          const float inv_n = 1.0f / (float)p.N;
+          const float mean = ts * inv_n;
+          const float rstd = rsqrtf(fmaxf(tq * inv_n - mean * mean, 0.f) + 1e-5f);
+          const float* gam = (row >= epi.p.ln_split && epi.p.ln_gamma_b) ? epi.p.ln_gamma_b : epi.p.ln_gamma;
+#pragma unroll 1
+          for (int c = c_first; c < BN / 64; c += c_step) {
+            const int col0 = n_blk * BN + c * 64;
+            float v[64];
+            epi.load_out_f32(row, col0, v);                                   // written by this very thread a moment ago (L1/L2 hit)
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * __ldg(gam + col0 + i);
+            Vec64<bf16>::store(reinterpret_cast<bf16*>(epi.p.ln_out) + row * epi.p.ld_ln + col0, v);
+          }
+        }
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (LNF) cluster_sync_all();                  // no CTA may exit while its peer can still write its shared memory
   if (warp == 1) { tc_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
 }
 

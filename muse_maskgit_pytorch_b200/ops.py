@@ -25,7 +25,8 @@ def _epi(out=None, ldo=0, bias=None, act=0, resid=None, ldr=0, row_stats=None, l
     return e
 
 
-def linear(a, w, out, epilogue=EPI_STORE, bias=None, act=0, resid=None, M=None, N=None, epi=None, row_stats=None, ln_width=0):
+def linear(a, w, out, epilogue=EPI_STORE, bias=None, act=0, resid=None, M=None, N=None, epi=None, row_stats=None, ln_width=0,
+           ln_out=None, ln_gamma=None, ln_gamma_b=None, ln_add=None, ln_split=None):
     """out = a @ w.T (+ epilogue).  a [M, K], w [N, K] same dtype (bf16 -> tcgen05, fp32 -> CUDA cores)."""
     _chk(a, "a"); _chk(w, "w")
     args = L.LinearArgs()
@@ -37,6 +38,10 @@ def linear(a, w, out, epilogue=EPI_STORE, bias=None, act=0, resid=None, M=None, 
     args.dtype = L.dt(a); args.epilogue = epilogue
     if epi is None:
         epi = _epi(out, out.stride(0), bias, act, resid, resid.stride(0) if resid is not None else 0, row_stats, ln_width)
+        if ln_out is not None:      # fused LayerNorm of the output rows (bf16) for the next matrix product
+            epi.ln_out = ln_out.data_ptr(); epi.ld_ln = ln_out.stride(0); epi.ln_gamma = ln_gamma.data_ptr()
+            epi.ln_gamma_b = L.ptr(ln_gamma_b); epi.ln_add = L.ptr(ln_add)
+            epi.ln_split = args.M if ln_split is None else ln_split
     args.epi = epi
     L.call("mmg_linear", args)
     return out

@@ -503,3 +503,25 @@ def test_logits_sample_philox_matches_oracle_stream():
     got = torch.stack([ids.cpu()[bi, mp[bi, j]] for bi in range(b) for j in range(nm)])
     assert torch.equal(got[margin > 1e-3], pred[margin > 1e-3]), (got.tolist(), pred.tolist())
     assert (got == pred).float().mean() > 0.9
+
+
+@pytest.mark.parametrize("N", [512, 128])
+def test_linear_residual_with_fused_layernorm(N):
+    """cluster-of-2 GEMM: x += a W^T (rows >= split also += add), ln_out = LN(x) * gamma (gamma_b for rows >= split),
+    row statistics buffer reset.  The two CTAs exchange (sum, sumsq) through distributed shared memory."""
+    M, K, split = 700, 256, 384
+    bf = torch.bfloat16
+    a, w = rnd("a", (M, K), bf), rnd("w", (N, K), bf, std=K ** -0.5)
+    x = rnd("x", (M, N)) * 2 + 0.3
+    ga, gb, add = 1 + 0.1 * rnd("ga", (N,)), 1 + 0.1 * rnd("gb", (N,)), rnd("add", (N,))
+    xd = dev(x); xn = torch.zeros((M, N), device="cuda", dtype=bf); stats = torch.ones((M, 2), device="cuda")
+    gad, gbd, addd = dev(ga), dev(gb), dev(add)
+    ops().linear(dev(a, bf), dev(w, bf), xd, epilogue=ops().EPI_RESIDUAL, resid=xd, row_stats=stats, ln_out=xn, ln_gamma=gad, ln_gamma_b=gbd, ln_add=addd, ln_split=split)
+    ref = x + a @ w.t()
+    ref[split:] += add
+    ok, msg = close(xd, ref, 3e-4)
+    assert ok, "x: " + msg
+    lref = torch.cat((F.layer_norm(ref[:split], (N,), ga, None), F.layer_norm(ref[split:], (N,), gb, None)))
+    ok, msg = close(xn, lref, 2e-2, 1e-2)
+    assert ok, "ln_out: " + msg
+    assert float(stats.abs().max()) == 0.
