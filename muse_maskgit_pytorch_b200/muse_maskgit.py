@@ -9,6 +9,7 @@ Both CFG branches of a decode step run as one batch of 2B sequences; the null br
 constant to_out(null_v) (every text key masked -> softmax puts weight exactly 1 on the null key).
 """
 import math
+import os
 from functools import partial
 from pathlib import Path
 from typing import Callable, List, Optional
@@ -241,7 +242,8 @@ class Transformer(nn.Module):
             e = torch.zeros((bn, self.dim), device=dev, dtype=torch.float32) if self_cond_embed is None else self_cond_embed.reshape(bn, -1).float().contiguous()
             for j in range(nb):
                 self._ff(e, sc, x[j * bn:(j + 1) * bn], ws, bn)
-        fused = adt == torch.bfloat16 and self.dim in (128, 256, 512) and all("w2f" in l["ff"] for l in P["layers"])
+        fused = (adt == torch.bfloat16 and self.dim in (128, 256, 512) and all("w2f" in l["ff"] for l in P["layers"])
+                 and os.environ.get("MMG_FUSE_LN", "1") != "0")
         live = [j for j in range(nb) if not ctx["all_masked"][j]]
         if fused and live == list(range(len(live))):
             return self._run_blocks_fused(P, ws, ctx, nb, b, n, len(live))
