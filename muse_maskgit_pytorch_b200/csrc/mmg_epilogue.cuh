@@ -256,16 +256,6 @@ struct Epilogue {
       for (int i = 0; i < 64; ++i) v[i] += r[i] + (p.bias ? __ldg(p.bias + col0 + i) : 0.f);
     }
   }
-  __device__ __forceinline__ void prep_store_f32(int col0, float (&v)[64]) const {     // STORE epilogue math without the store
-    if (p.bias) {
-#pragma unroll
-      for (int i = 0; i < 64; ++i) v[i] += __ldg(p.bias + col0 + i);
-    }
-    if (p.act == 1) {
-#pragma unroll
-      for (int i = 0; i < 64; ++i) v[i] = leaky01(v[i]);
-    }
-  }
   __device__ __forceinline__ void load_out_f32(int64_t row, int col0, float (&v)[64]) const {
     Vec64<float>::load(reinterpret_cast<const float*>(p.out) + row * p.ldo + col0, v);
   }

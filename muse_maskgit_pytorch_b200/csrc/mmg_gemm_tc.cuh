@@ -20,8 +20,8 @@ namespace mmg {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 384;          // warpgroup 0: warp 0 TMA, warp 1 MMA (2, 3 idle); warpgroups 1-2: 8 epilogue warps
+constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_MAX_TAPS = 16;
 
 struct alignas(64) TcGemmParams {
@@ -42,8 +42,7 @@ template <int BN> struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_STAGE_BYTES = TC_EPI_WARPS * 4096;      // per epilogue warp: one 32 x 32 fp32 transpose block
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + OUT_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -63,7 +62,6 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES + 256;     // [TC_EPI_WARPS][32 rows][128 B], 16-byte chunks XOR-swizzled by row
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = LNF ? p.num_m_tiles : p.num_m_tiles * p.num_n_tiles;      // LNF: this CTA walks m-blocks, n-block = cluster rank
@@ -162,29 +160,6 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     if (epi.kind == MMG_EPI_QKV) { epi.p.q_scale = s_scale; epi.p.k_scale = s_scale + 64; }
     const bool whole_row = (epi.kind == MMG_EPI_CONVT_RGB);      // needs every chunk of a row in one thread
     const bool prefetch_resid = epi.can_prefetch_resid();
-    // Coalesced fp32 output: the accumulator arrives one ROW per lane; a warp-private shared-memory transpose (16-byte chunks
-    // XOR-swizzled by row, conflict-free both ways, __syncwarp only) turns every global store instruction into 4 complete
-    // 128-byte lines instead of 32 scattered 32-byte sectors.
-    float* my_stage = reinterpret_cast<float*>(out_stage + (warp - 4) * 4096);
-    const bool coalesce_f32 = p.mode == 0 && (epi.p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(epi.p.out) & 15) == 0 &&
-                              ((epi.kind == MMG_EPI_STORE && epi.p.out_dtype == MMG_F32) || prefetch_resid);
-    auto store_rows_f32 = [&](int64_t row0, int col0, const float (&v)[64]) {
-      float* outp = reinterpret_cast<float*>(epi.p.out);
-#pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {                         // two 32-column blocks of the 64-column chunk
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(my_stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[hb * 32 + 4 * j], v[hb * 32 + 4 * j + 1], v[hb * 32 + 4 * j + 2], v[hb * 32 + 4 * j + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + (lane >> 3), jj = lane & 7;
-          const float4 t = *reinterpret_cast<const float4*>(my_stage + rr * 32 + ((jj ^ (rr & 7)) << 2));
-          if (row0 + rr < p.M) *reinterpret_cast<float4*>(outp + (row0 + rr) * epi.p.ldo + col0 + hb * 32 + jj * 4) = t;
-        }
-      }
-    };
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t stats_phase = 0; int stats_buf = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -230,14 +205,11 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
 #pragma unroll
               for (int i = 0; i < 64; ++i) { ln_sum += v[i]; ln_sq = fmaf(v[i], v[i], ln_sq); }
             }
-            if (!coalesce_f32) epi.store_f32(row, col0, v);
-          } else if (coalesce_f32) {
-            epi.prep_store_f32(col0, v);                    // bias / activation, no store
+            epi.store_f32(row, col0, v);
           } else {
             epi.template apply<true>(row, col0, v, 64);
           }
         }
-        if (coalesce_f32 && col0 < p.N) store_rows_f32(row - lane, col0, v);   // warp-collective: all 32 lanes (valid or not) take part
       }
       if (valid && mine) epi.end_row(row);
       tc_fence_before();
