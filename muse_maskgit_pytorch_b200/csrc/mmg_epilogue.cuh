@@ -183,9 +183,10 @@ struct Epilogue {
         else if (hc < p.nq_heads + p.nk_heads) { h = hc - p.nq_heads; dst = p.k_out; off = ((b * p.heads + h) * (int64_t)p.kv_rows + p.key_off + t) * 64; sc = p.k_scale; }
         else { h = hc - p.nq_heads - p.nk_heads; dst = p.v_out; off = ((b * p.heads + h) * (int64_t)p.kv_rows + p.key_off + t) * 64; }
         if (sc) {  // F.normalize(dim=-1, eps=1e-12) then * scale   (muse_maskgit_pytorch.py:151-153)
-          float ss = 0.f;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};                    // four partial sums: 16-deep dependency chains instead of 64
 #pragma unroll
-          for (int i = 0; i < 64; ++i) ss += v[i] * v[i];
+          for (int i = 0; i < 64; ++i) s4[i & 3] = fmaf(v[i], v[i], s4[i & 3]);
+          const float ss = (s4[0] + s4[1]) + (s4[2] + s4[3]);
           const float inv = FAST ? rsqrtf(fmaxf(ss, 1e-24f)) : 1.0f / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
           for (int i = 0; i < 64; ++i) v[i] = v[i] * inv * sc[i];

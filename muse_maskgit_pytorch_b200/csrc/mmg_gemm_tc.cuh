@@ -184,6 +184,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       if (valid && mine) epi.begin_row(row);
+      bool released = false;
 #pragma unroll 1
       for (int c = c_first; c < BN / 64; c += c_step) {
         if (!mine) break;
@@ -191,6 +192,12 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         tmem_ld_32x32b_x32(t_row + c * 64, v);
         tmem_ld_32x32b_x32(t_row + c * 64 + 32, v + 32);
         tmem_ld_wait();
+        if (c + c_step >= BN / 64) {               // last chunk is in registers: hand the accumulator stage back before the math
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + acc);
+          released = true;
+        }
         const int col0 = n_blk * BN + c * 64;
         if (valid && col0 < p.N) {
           if (prefetch_resid) {
@@ -212,9 +219,11 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         }
       }
       if (valid && mine) epi.end_row(row);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      if (!released) {                             // warps that own no chunk of this tile
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + acc);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (LNF) {
         // ---- LayerNorm of the freshly written row: exchange (sum, sumsq) partials with the CTA that owns the other column half ----
