@@ -122,15 +122,29 @@ layernorm_vec_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* 
       for (int j = 0; j < VN; ++j) v[i][j] = 0.f;
     }
   }
-  const float mean = warp_sum(sum) / (float)width;
-  float sq = 0.f;
+  float mean, rstd;
+  if (sizeof(TY) == 2) {
+    // bf16 output: one fused reduction of (sum, sum of squares) — the E[x^2] - mean^2 form is far inside bf16 output precision
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    const int c = (i * 32 + lane) * VN;
+    for (int i = 0; i < CH; ++i)
 #pragma unroll
-    for (int j = 0; j < VN; ++j) if (c + j < width) { const float d = v[i][j] - mean; sq += d * d; }
+      for (int j = 0; j < VN; ++j) sq = fmaf(v[i][j], v[i][j], sq);       // padded / out-of-width entries are 0
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+    mean = sum / (float)width;
+    rstd = rsqrtf(fmaxf(sq / (float)width - mean * mean, 0.f) + 1e-5f);
+  } else {
+    mean = warp_sum(sum) / (float)width;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = (i * 32 + lane) * VN;
+#pragma unroll
+      for (int j = 0; j < VN; ++j) if (c + j < width) { const float d = v[i][j] - mean; sq += d * d; }
+    }
+    rstd = rsqrtf(warp_sum(sq) / (float)width + 1e-5f);
   }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)width + 1e-5f);
   TY* yr = y + row * ldy;
 #pragma unroll
   for (int i = 0; i < CH; ++i) {

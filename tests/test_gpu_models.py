@@ -228,3 +228,23 @@ def test_generate_bf16_philox_shapes_and_determinism():
     mg.transformer.encode_text = lambda texts: te[1:1 + len(texts)]
     _, idc = mg.generate(texts=["a"] * 2, timesteps=8, return_ids=True)
     assert torch.equal(idc, ida[1:])
+
+
+def test_muse_cascade_runs_on_device():
+    """Muse(base, superres): base generate -> superres generate conditioned on the low-res images (kept on the device)."""
+    m = M()
+    base = make_maskgit("bf16")
+    sup = make_maskgit("bf16", superres=True)
+    te = util.text_embeds("g4.te", 3, 8, 128, 14).cuda()
+    base.transformer.encode_text = lambda texts: te[:len(texts)]
+    sup.transformer.encode_text = lambda texts: te[:len(texts)]
+    base.sampler_seed, sup.sampler_seed = 7, 8
+    muse = m.Muse(base=base, superres=sup)
+    hi, lo = muse(["a", "b"], timesteps=6, return_lowres=True, return_pil_images=False)
+    assert lo.shape == (2, 3, 16, 16) and hi.shape == (2, 3, 32, 32) and torch.isfinite(hi).all()
+    pil = muse(["a", "b"], timesteps=4, return_pil_images=True)
+    assert len(pil) == 2 and pil[0].size == (32, 32)
+    # the cascade equals the two generate() calls made by hand
+    lo2 = base.generate(["a", "b"], timesteps=6, cond_scale=3., temperature=1.)
+    hi2 = sup.generate(["a", "b"], cond_images=lo2, timesteps=6, cond_scale=3., temperature=1.)
+    assert torch.equal(lo, lo2) and torch.equal(hi, hi2)
