@@ -229,8 +229,34 @@ typedef struct {
   uint64_t seed; uint64_t step; int64_t row_offset;  /* global row = row_offset + b*n + pos                        */
   const uint64_t* seed_dev;  /* optional device word added to `seed` at run time (lets a captured CUDA graph be replayed
                                 with a fresh seed)                                                                   */
+  int64_t mask_id; int32_t only_masked;         /* only_masked != 0: ids[b, pos] is replaced only where it equals mask_id (the
+                                `where(is_mask, pred_ids, ids)` of :582-588 when rows of already-decoded positions are scored
+                                too, can_remask_prev_masked = True); scores are written for every listed row              */
+  int32_t rng_mode;          /* u == NULL only.  0: the keying above.  1: the stream ATen's CUDA `zeros_like(t).uniform_(0, 1)` draws
+                                for the reference's [B_global, n, V] noise tensor (muse_maskgit_pytorch.py:407) from a generator with
+                                seed (seed + *seed_dev) and offset (aten_offset + *aten_offset_dev): element i = t + aten_stride*k is
+                                word k&3 of Philox(counter = offset/4 + k/4, subsequence = t) * 2^-32 + 2^-33, 1 -> 0; aten_stride =
+                                256 * min(SMs * maxThreadsPerSM/256, ceil(numel/256)); accurate logf / IEEE division as with `u`  */
+  uint64_t aten_offset; const uint64_t* aten_offset_dev; uint32_t aten_stride, _pad;
 } mmg_logits_sample_args;
 int mmg_logits_sample(const mmg_logits_sample_args* a, void* stream);
+
+/* token-critic scoring branch of MaskGit.generate (muse_maskgit_pytorch.py:590-600; TokenCritic :383-386, SelfCritic :352-361):
+ *   s[r] = dot(LayerNorm(x_cond[r]) * gamma, w) + bias;   x_null != NULL: s = s_null + (s - s_null) * cond_scale  (CFG, :257)
+ *   scores[r] = s + (u[r] - 0.5) * noise_mul       noise_mul = critic_noise_scale * steps_until_x0 / timesteps
+ * x_* are the residual streams after the critic's last block (the final LayerNorm and the 1-wide head are applied here).
+ * u == NULL: u = Philox4x32-10(counter = (0xFFFFFFFF, step, row_offset + r), key = seed + *seed_dev) >> 8 * 2^-24.            */
+typedef struct {
+  const float* x_cond; const float* x_null;   /* [rows, dim] fp32; x_null may be NULL (cond_scale == 1, SelfCritic)   */
+  const float* gamma; const float* w;         /* [dim] final LayerNorm gain, [dim] head weight (to_logits / to_pred)  */
+  float bias, cond_scale, noise_mul; int32_t dim;
+  const float* u;                             /* [rows] injected uniforms or NULL                                     */
+  float* scores;                              /* [rows] out                                                           */
+  int64_t rows, row_offset; uint64_t seed; const uint64_t* seed_dev; int32_t step;
+  int32_t rng_mode;                           /* 1: ATen's `uniform(scores.shape)` stream (:598), see mmg_logits_sample_args */
+  uint64_t aten_offset; const uint64_t* aten_offset_dev; uint32_t aten_stride, _pad;
+} mmg_critic_score_args;
+int mmg_critic_score(const mmg_critic_score_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * VQ lookup.  replaces the quantizer calls at vqgan_vae.py:424 and 429-435.

@@ -10,7 +10,7 @@ extern "C" int64_t mmg_launch_count(void) { return mmg::launch_counter().load();
 extern "C" int mmg_sizeof(const char* name) {
 #define SZ(n) if (!strcmp(name, "mmg_" #n)) return (int)sizeof(mmg_##n##_args)
   SZ(linear); SZ(conv2d); SZ(conv_transpose2d); SZ(conv_in); SZ(groupnorm); SZ(layernorm); SZ(embed); SZ(attention);
-  SZ(remask); SZ(final_embed); SZ(logits_sample); SZ(vq_lfq_encode); SZ(vq_l2_argmin); SZ(vq_decode_codes); SZ(cast);
+  SZ(remask); SZ(final_embed); SZ(logits_sample); SZ(vq_lfq_encode); SZ(vq_l2_argmin); SZ(vq_decode_codes); SZ(cast); SZ(critic_score);
 #undef SZ
   if (!strcmp(name, "mmg_epilogue")) return (int)sizeof(mmg_epilogue_args);
   return 0;

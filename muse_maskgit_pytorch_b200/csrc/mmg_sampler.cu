@@ -44,6 +44,31 @@ __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint3
   return c0;
 }
 
+// Philox4x32-10, all four output words
+__device__ __forceinline__ uint4 philox4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// The value ATen's CUDA `uniform_(0, 1)` writes at flat index t + stride * k of an fp32 tensor (generator seed / offset):
+// word (k & 3) of Philox(counter = offset/4 + (k >> 2), subsequence = t), mapped like curand_uniform4 (w * 2^-32 + 2^-33, in
+// (0, 1]) and then 1 -> 0.  (DistributionTemplates.h: distribution_elementwise_grid_stride_kernel + uniform_kernel.)
+__device__ __forceinline__ float aten_uniform(uint32_t t, uint64_t k, uint64_t off4, uint64_t seed) {
+  const uint64_t ctr = off4 + (k >> 2);
+  const uint4 w4 = philox4((uint32_t)ctr, (uint32_t)(ctr >> 32), t, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t ii = (uint32_t)k & 3u;
+  const uint32_t w = ii == 0 ? w4.x : ii == 1 ? w4.y : ii == 2 ? w4.z : w4.w;
+  const float u = fmaf(__uint2float_rn(w), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  return u == 1.0f ? 0.0f : u;
+}
+
 __device__ __forceinline__ bool better(float v, int vi, float w, int wi) { return v > w || (v == w && vi < wi); }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float key_to_float(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
@@ -59,9 +84,10 @@ __device__ __forceinline__ void block_sum2(int a, int b, int* red, int warp, int
   for (int w = 0; w < SMP_THREADS / 32; ++w) { oa += red[w]; ob += red[32 + w]; }
 }
 
-// EXACT = injected-noise parity mode: IEEE division and accurate logf so the perturbed values match the reference's
-// fp32 arithmetic as closely as a GPU can; otherwise (in-kernel Philox) fast MUFU-based logs and a reciprocal multiply.
-template <bool EXACT>
+// MODE 1 = injected-noise parity mode, MODE 2 = ATen-compatible in-kernel Philox (the stream a seeded torch.cuda run of the
+// reference draws): IEEE division and accurate logf so the perturbed values match the reference's fp32 arithmetic as closely
+// as a GPU can; MODE 0 (libmmg's own Philox keying) uses fast MUFU-based logs and a reciprocal multiply.
+template <int MODE>
 __global__ void __launch_bounds__(SMP_THREADS)
 logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   extern __shared__ uint8_t smraw[];
@@ -301,6 +327,12 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   const int64_t grow = a.row_offset + (int64_t)b * a.n + pos;
   const uint64_t seed = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
   const float inv_t = 1.0f / tdiv;
+  uint64_t aq0 = 0, aoff4 = 0; uint32_t ar0 = 0;
+  if (MODE == 2) {            // flat index of logit (grow, v) in the reference's [B, n, V] noise tensor = grow * V + v = ar0 + v + S * aq0
+    const uint64_t base = (uint64_t)grow * (uint64_t)V;
+    aq0 = base / a.aten_stride; ar0 = (uint32_t)(base - aq0 * a.aten_stride);
+    aoff4 = (a.aten_offset + (a.aten_offset_dev ? *a.aten_offset_dev : 0ull)) >> 2;
+  }
   constexpr int PER = (SMP_CAP + SMP_THREADS - 1) / SMP_THREADS;
   float pv[PER];
 #pragma unroll
@@ -309,8 +341,10 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
     float p = -FLT_MAX;
     if (s < n) {
       const int v = lidx[s];
-      if (EXACT) {
-        const float u = a.u[((int64_t)b * a.n + pos) * V + v];
+      if (MODE != 0) {
+        float u;
+        if (MODE == 1) u = a.u[((int64_t)b * a.n + pos) * V + v];
+        else { const uint32_t r = ar0 + (uint32_t)v, dq = r / a.aten_stride; u = aten_uniform(r - dq * a.aten_stride, aq0 + dq, aoff4, seed); }
         const float l1 = logf(fmaxf(u, 1e-20f));
         p = __fdiv_rn(lval[s], tdiv) - logf(fmaxf(-l1, 1e-20f));
       } else {
@@ -358,7 +392,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   if (tid == 0) {
     if (win_v < 0) { win_v = 0; win_x = row[0]; }                 // degenerate rows (all -inf / NaN)
     const float p = expf(win_x - s_max) / s_sum;
-    a.ids[(int64_t)b * a.n + pos] = win_v;
+    if (!a.only_masked || a.ids[(int64_t)b * a.n + pos] == a.mask_id) a.ids[(int64_t)b * a.n + pos] = win_v;
     a.scores[(int64_t)b * a.n + pos] = 1.0f - p;
   }
 }
@@ -401,6 +435,49 @@ remask_kernel(int64_t* __restrict__ ids, float* __restrict__ scores, int32_t* __
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// token-critic scores (muse_maskgit_pytorch.py:590-600): per sequence position, the dim_out = 1 head applied to the
+// final-LayerNorm embedding of the critic's forward(s), CFG-combined, plus annealed uniform noise.  One warp per row.
+//   s = dot(LN(x_cond)*gamma, w) [+ bias];  if x_null: s = s_null + (s - s_null) * cond_scale;  s += (u - 0.5) * noise_mul
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float critic_head(const float* __restrict__ xr, const float* __restrict__ gamma, const float* __restrict__ w, int dim, int lane) {
+  float sum = 0.f;
+  for (int c = lane; c < dim; c += 32) sum += xr[c];
+  const float mean = warp_sum(sum) / (float)dim;
+  float sq = 0.f, dot = 0.f;
+  for (int c = lane; c < dim; c += 32) { const float d = xr[c] - mean; sq += d * d; dot += d * __ldg(gamma + c) * __ldg(w + c); }
+  sq = warp_sum(sq); dot = warp_sum(dot);
+  return dot * rsqrtf(sq / (float)dim + 1e-5f);
+}
+
+__global__ void __launch_bounds__(256)
+critic_score_kernel(mmg_critic_score_args a) {
+  pdl_wait(); pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= a.rows) return;
+  float s = critic_head(a.x_cond + row * a.dim, a.gamma, a.w, a.dim, lane) + a.bias;
+  if (a.x_null) {
+    const float sn = critic_head(a.x_null + row * a.dim, a.gamma, a.w, a.dim, lane) + a.bias;
+    s = sn + (s - sn) * a.cond_scale;
+  }
+  if (lane == 0) {
+    float u;
+    if (a.u) u = a.u[row];
+    else {
+      const uint64_t seed = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
+      const int64_t grow = a.row_offset + row;
+      if (a.rng_mode == 1) {      // ATen stream of `uniform(scores.shape)`: flat index = global position
+        const uint64_t k = (uint64_t)grow / a.aten_stride;
+        u = aten_uniform((uint32_t)((uint64_t)grow - k * a.aten_stride), k, (a.aten_offset + (a.aten_offset_dev ? *a.aten_offset_dev : 0ull)) >> 2, seed);
+      } else
+        u = (float)(philox_first(0xFFFFFFFFu, (uint32_t)a.step, (uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), (uint32_t)seed, (uint32_t)(seed >> 32)) >> 8) * (1.0f / 16777216.0f);
+    }
+    a.scores[row] = s + (u - 0.5f) * a.noise_mul;
+  }
+}
+
 }  // namespace mmg
 
 using namespace mmg;
@@ -413,12 +490,17 @@ extern "C" int mmg_logits_sample(const mmg_logits_sample_args* a, void* stream) 
   const int64_t R = (int64_t)a->B * a->num_masked;
   if (R == 0) return MMG_OK;
   static const size_t smem = (size_t)SMP_CAP * 8 + (size_t)SMP_THREADS * 64;
-  static cudaError_t attr0 = cudaFuncSetAttribute(logits_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  static cudaError_t attr1 = cudaFuncSetAttribute(logits_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (attr0 != cudaSuccess || attr1 != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(logits_sample): %s", cudaGetErrorString(attr0 != cudaSuccess ? attr0 : attr1));
+  MMG_CHECK_ARG(a->rng_mode == 0 || (a->rng_mode == 1 && a->aten_stride >= 256 && a->aten_stride % 256 == 0 && a->aten_offset % 4 == 0 && !a->u),
+                "mmg_logits_sample: rng_mode=%d aten_stride=%u", a->rng_mode, a->aten_stride);
+  static cudaError_t attr0 = cudaFuncSetAttribute(logits_sample_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static cudaError_t attr1 = cudaFuncSetAttribute(logits_sample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static cudaError_t attr2 = cudaFuncSetAttribute(logits_sample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (attr0 != cudaSuccess || attr1 != cudaSuccess || attr2 != cudaSuccess)
+    return fail(MMG_ECUDA, "cudaFuncSetAttribute(logits_sample): %s", cudaGetErrorString(attr0 != cudaSuccess ? attr0 : attr1 != cudaSuccess ? attr1 : attr2));
   float t = a->temperature; if (t < 1e-10f) t = 1e-10f;      // max(temperature, 1e-10): muse_maskgit_pytorch.py:411
-  if (a->u) MMG_CUDA(launch_pdl(logits_sample_kernel<true>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, *a, t));
-  else MMG_CUDA(launch_pdl(logits_sample_kernel<false>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, *a, t));
+  if (a->u) MMG_CUDA(launch_pdl(logits_sample_kernel<1>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, *a, t));
+  else if (a->rng_mode == 1) MMG_CUDA(launch_pdl(logits_sample_kernel<2>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, *a, t));
+  else MMG_CUDA(launch_pdl(logits_sample_kernel<0>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, *a, t));
   MMG_LAUNCHED();
   return MMG_OK;
 }
@@ -429,6 +511,17 @@ extern "C" int mmg_remask(const mmg_remask_args* a, void* stream) {
   MMG_CHECK_ARG(a->n > 0 && a->num_masked >= 1 && a->num_masked <= a->n && a->n <= 16384, "mmg_remask: n=%d num_masked=%d", a->n, a->num_masked);
   if (a->B == 0) return MMG_OK;
   MMG_CUDA(launch_pdl(remask_kernel, dim3(a->B), dim3(256), (size_t)a->n * 8, st, a->ids, a->scores, a->masked_pos, a->n, a->num_masked, a->mask_id));
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
+extern "C" int mmg_critic_score(const mmg_critic_score_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MMG_CHECK_ARG(a && a->x_cond && a->gamma && a->w && a->scores, "mmg_critic_score: NULL pointer");
+  MMG_CHECK_ARG(a->dim > 0 && a->rows >= 0, "mmg_critic_score: dim=%d", a->dim);
+  MMG_CHECK_ARG(a->rng_mode == 0 || (a->rng_mode == 1 && a->aten_stride >= 256 && a->aten_offset % 4 == 0), "mmg_critic_score: rng_mode=%d aten_stride=%u", a->rng_mode, a->aten_stride);
+  if (a->rows == 0) return MMG_OK;
+  MMG_CUDA(launch_pdl(critic_score_kernel, dim3((unsigned)((a->rows + 7) / 8)), dim3(256), 0, st, *a));
   MMG_LAUNCHED();
   return MMG_OK;
 }

@@ -149,6 +149,7 @@ class Transformer(nn.Module):
         P["gf"] = f32(tb.norm.gamma)
         P["tok"], P["pos"] = f32(self.token_emb.weight), f32(self.pos_emb.weight)
         P["wlog"] = wa(self.to_logits.weight)
+        P["whead"] = f32(self.to_logits.weight).reshape(-1) if self.dim_out == 1 else None     # TokenCritic head, applied in mmg_critic_score
         P["wproj"] = wa(self.text_embed_proj.weight) if isinstance(self.text_embed_proj, nn.Linear) else None
         P["sc"] = ff_pack(self.self_cond_to_init_embed) if self.self_cond else None
         self._pack = P
@@ -202,9 +203,9 @@ class Transformer(nn.Module):
     # ----- the block stack over R = nb*b*n rows -------------------------------------------------------------------------
     def _workspace(self, nb, b, n, dev):
         key = (nb, b, n, str(dev), self._adt())
-        ws = getattr(self, "_ws", None)
-        if ws is not None and ws["key"] == key:
-            return ws
+        cache = self.__dict__.setdefault("_ws", {})        # a few shapes stay resident (e.g. 2-branch decode + 1-branch self-critic)
+        if key in cache:
+            return cache[key]
         P = self._packed()
         adt, tb = P["adt"], self.transformer_blocks
         heads, dim, inner = tb.heads, self.dim, tb.heads * 64
@@ -221,7 +222,9 @@ class Transformer(nn.Module):
                   h=torch.empty((R, Fp), device=dev, dtype=adt),
                   hn=torch.empty((R, Fp), device=dev, dtype=adt),
                   stats=torch.zeros((R, 2), device=dev, dtype=torch.float32))
-        self._ws = ws
+        if len(cache) >= 4:
+            cache.pop(next(iter(cache)))
+        cache[key] = ws
         return ws
 
     def _run_blocks(self, ids, ctx, nb, self_cond_embed=None):
@@ -236,12 +239,15 @@ class Transformer(nn.Module):
         ws = self._workspace(nb, b, n, dev)
         x, xn, q, k, v, ao = ws["x"], ws["xn"], ws["q"], ws["k"], ws["v"], ws["ao"]
         R, bn = nb * b * n, b * n
-        ops.embed(ids.contiguous(), P["tok"], P["pos"], x, n=n, copies=nb)
-        if self.self_cond:
-            sc = P["sc"]
-            e = torch.zeros((bn, self.dim), device=dev, dtype=torch.float32) if self_cond_embed is None else self_cond_embed.reshape(bn, -1).float().contiguous()
-            for j in range(nb):
-                self._ff(e, sc, x[j * bn:(j + 1) * bn], ws, bn)
+        if self.self_cond and self_cond_embed is not None:
+            # x += self_cond_to_init_embed(embed of the previous step), identical for every CFG branch (muse_maskgit_pytorch.py:325-328);
+            # a missing embed is zeros in the reference and FeedForward(0) == 0 exactly, so that case adds nothing
+            ops.embed(ids.contiguous(), P["tok"], P["pos"], x[:bn], n=n, copies=1)
+            self._ff(self_cond_embed.reshape(bn, -1).float().contiguous(), P["sc"], x[:bn], ws, bn)
+            for j in range(1, nb):
+                x[j * bn:(j + 1) * bn].copy_(x[:bn])
+        else:
+            ops.embed(ids.contiguous(), P["tok"], P["pos"], x, n=n, copies=nb)
         fused = (adt == torch.bfloat16 and self.dim in (128, 256, 512) and all("w2f" in l["ff"] for l in P["layers"])
                  and os.environ.get("MMG_FUSE_LN", "0") == "1")   # opt-in: measured equal at batch 64 and slower at batch 8
         live = [j for j in range(nb) if not ctx["all_masked"][j]]
@@ -403,6 +409,44 @@ class TokenCritic(Transformer):
         super().__init__(*args, dim_out=1, **kwargs)
 
 
+class SelfCritic(nn.Module):
+    """ref: muse_maskgit_pytorch.py:352-375 — the generator itself as critic: to_pred(embed of the conditional forward)."""
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+        self.to_pred = nn.Linear(net.dim, 1)
+        self._head_cache = None
+
+    def _apply(self, fn, *a, **k):
+        self._head_cache = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._head_cache = None
+        return super().load_state_dict(*a, **k)
+
+    def _head(self):
+        if self._head_cache is None:          # one host read of the bias per weight load, not per generate()
+            self._head_cache = (self.to_pred.weight.detach().float().reshape(-1).contiguous(), float(self.to_pred.bias.detach().float().item()))
+        return self._head_cache
+
+    @torch.no_grad()
+    def forward_with_cond_scale(self, x, *args, **kwargs):
+        _, embeds = self.net.forward_with_cond_scale(x, *args, return_embed=True, **kwargs)
+        return embeds @ self.to_pred.weight.float().t() + self.to_pred.bias.float()
+
+    @torch.no_grad()
+    def forward(self, x, *args, labels=None, **kwargs):
+        _, embeds = self.net(x, *args, return_embed=True, **kwargs)
+        logits = embeds @ self.to_pred.weight.float().t() + self.to_pred.bias.float()
+        if labels is None:
+            return logits
+        return torch.nn.functional.binary_cross_entropy_with_logits(logits[..., 0], labels)
+
+    def forward_with_neg_prompt(self, x, *args, **kwargs):
+        return self.net.forward_with_neg_prompt(x, *args, **kwargs)
+
+
 def cosine_schedule(t):
     return torch.cos(t * math.pi * 0.5)
 
@@ -432,12 +476,18 @@ class MaskGit(nn.Module):
         assert not (self_token_critic and token_critic is not None)
         self.token_critic = token_critic
         if self_token_critic:
-            raise NotImplementedError("self token critic is not part of the accelerated path yet (SURVEY.md 8f #3)")
+            self.token_critic = SelfCritic(transformer)
         self.critic_loss_weight, self.self_cond_prob, self.no_mask_token_prob = critic_loss_weight, self_cond_prob, no_mask_token_prob
         # sampler noise: None -> in-kernel Philox keyed on (seed, global row, vocab index); or a callable
-        # noise_fn(step, shape) -> U[0,1) tensor [b, n, V] (parity mode: the tensor the reference would draw)
+        # noise_fn(step, shape) -> U[0,1) tensor (parity mode: the tensors the reference would draw, in its order:
+        # shape (b, n, V) for the gumbel noise, then shape (b, n) for the token-critic noise when a critic scores the step)
         self.sampler_seed = None            # None: one draw from torch's global generator per call (reproducible under manual_seed)
         self.sampler_noise_fn = None
+        # "mmg": libmmg's Philox keying (invariant to the GPU count).  "aten": the exact stream the reference's
+        # `zeros_like(t).uniform_(0, 1)` / `uniform(scores.shape)` calls draw from torch's CUDA generator on this device, consumed
+        # from (and advanced on) torch.cuda's default generator, with the reference's accurate log / division arithmetic
+        self.sampler_rng = "mmg"
+        self.global_batch = None            # "aten" + batch sharding: size of the whole batch the reference would have drawn noise for
         self.use_cuda_graph = True
         self._graphs = {}
         self.row_offset = 0                 # global index of this shard's first sequence (multi-GPU batch sharding)
@@ -473,13 +523,9 @@ class MaskGit(nn.Module):
         tr = self.transformer
         if negative_texts is not None:
             raise NotImplementedError("negative_texts raises TypeError in the reference (defect B2); not supported")
-        if self.token_critic is not None and not force_not_use_token_critic:
-            raise NotImplementedError("token-critic scoring is not part of the accelerated path yet (SURVEY.md 8f #3)")
-        if can_remask_prev_masked:
+        use_critic = self.token_critic is not None and not force_not_use_token_critic
+        if can_remask_prev_masked and not use_critic:      # the reference only reaches this assert in the no-critic branch (:611-612)
             assert self.no_mask_token_prob > 0., "without training with some of the non-masked tokens forced to predict, not sure if the logits will be meaningful for these token"
-            raise NotImplementedError("can_remask_prev_masked=True is not implemented in the masked-rows-only sampler")
-        if self.self_cond:
-            raise NotImplementedError("self-conditioning feedback is not part of the accelerated path yet (SURVEY.md 8f #3)")
         fmap_size = fmap_size if fmap_size is not None else self.vae.get_encoded_fmap_size(self.image_size)
         device = next(self.parameters()).device
         b = len(texts)
@@ -490,20 +536,30 @@ class MaskGit(nn.Module):
         else:
             cond_images = None
         # per-call seed: explicit sampler_seed, else one draw from torch's global generator (reproducible under manual_seed)
-        seed = self.sampler_seed if self.sampler_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        assert self.sampler_rng in ("mmg", "aten"), self.sampler_rng
         if getattr(self, "_seed_dev", None) is None or self._seed_dev.device != device:
             self._seed_dev = torch.zeros((1,), dtype=torch.int64, device=device)
-        self._seed_dev.fill_(seed)
+        aten = None
+        if self.sampler_rng == "aten" and self.sampler_noise_fn is None:
+            aten = self._aten_plan(device, b, fmap_size ** 2, tr.num_tokens, timesteps, use_critic)
+        else:
+            seed = self.sampler_seed if self.sampler_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+            self._seed_dev.fill_(seed)
         body = partial(self._generate_body, fmap_size=fmap_size, temperature=temperature, topk_filter_thres=topk_filter_thres,
-                       timesteps=timesteps, cond_scale=cond_scale, b=b)
+                       timesteps=timesteps, cond_scale=cond_scale, b=b, use_critic=use_critic, critic_noise_scale=critic_noise_scale,
+                       score_all=bool(can_remask_prev_masked) and not use_critic, aten=aten)
+        critic_net = self.token_critic if isinstance(self.token_critic, Transformer) and use_critic else None
         if not self.use_cuda_graph or self.sampler_noise_fn is not None:
             images, ids = body(text_embeds, cond_images)
             return (images, ids) if return_ids else images
         # ---- whole-call CUDA graph: 18 decode steps + VAE decode replayed as one launch (no per-kernel host work) ----
         key = (b, tuple(text_embeds.shape), text_embeds.dtype, None if cond_images is None else tuple(cond_images.shape), fmap_size,
-               float(temperature), float(topk_filter_thres), int(timesteps), float(cond_scale), int(self.row_offset), tr.precision, self.vae.precision)
+               float(temperature), float(topk_filter_thres), int(timesteps), float(cond_scale), int(self.row_offset), tr.precision, self.vae.precision,
+               use_critic, float(critic_noise_scale), bool(can_remask_prev_masked), None if aten is None else aten["key"])
+        pack_ids = lambda: (id(tr._pack), id(self.vae._pack), id(self.cond_vae._pack), id(critic_net._pack) if critic_net is not None else 0,
+                            id(self.token_critic._head_cache) if isinstance(self.token_critic, SelfCritic) else 0)
         entry = self._graphs.get(key)
-        if entry is not None and entry[5] != (id(tr._pack), id(self.vae._pack), id(self.cond_vae._pack)):
+        if entry is not None and entry[5] != pack_ids():
             entry = None                                       # weights were re-packed (load_state_dict / .to()): re-capture
         if entry is None:
             te_s = text_embeds.clone()
@@ -514,8 +570,10 @@ class MaskGit(nn.Module):
             with torch.cuda.graph(graph):
                 out_images, out_ids = body(te_s, ci_s)
             # the entry keeps alive everything the captured kernels point at (packed weights, workspaces)
-            entry = (graph, te_s, ci_s, out_images, out_ids, (id(tr._pack), id(self.vae._pack), id(self.cond_vae._pack)),
-                     (tr._pack, self.vae._pack, self.cond_vae._pack, tr._ws))
+            entry = (graph, te_s, ci_s, out_images, out_ids, pack_ids(),
+                     (tr._pack, self.vae._pack, self.cond_vae._pack, dict(tr._ws),
+                      None if critic_net is None else (critic_net._pack, dict(critic_net._ws)),
+                      self.token_critic._head_cache if isinstance(self.token_critic, SelfCritic) else None))
             if len(self._graphs) >= 4:
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = entry
@@ -527,7 +585,29 @@ class MaskGit(nn.Module):
         images, ids = out_images.clone(), out_ids.clone()
         return (images, ids) if return_ids else images
 
-    def _generate_body(self, text_embeds, cond_images, *, fmap_size, temperature, topk_filter_thres, timesteps, cond_scale, b):
+    def _aten_plan(self, device, b, n, V, timesteps, use_critic):
+        """Offsets of the reference's uniform_ calls in torch's CUDA Philox stream (one (b, n, V) gumbel draw, then one (b, n) critic
+        draw per step, muse_maskgit_pytorch.py:407, 598).  Launch geometry as ATen's calc_execution_policy: block 256,
+        grid = min(SMs * maxThreadsPerSM / 256, ceil(numel / 256)), 4 values per thread and round.  The generator is read here and
+        advanced by what the reference would have consumed; seed / offset reach the kernels through device words (graph replay)."""
+        gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+        props = torch.cuda.get_device_properties(device)
+        cap = props.multi_processor_count * (props.max_threads_per_multi_processor // 256)
+        B = self.global_batch if self.global_batch is not None else b
+        stride = lambda numel: 256 * min(cap, (numel + 255) // 256)
+        inc = lambda numel: ((numel - 1) // (stride(numel) * 4) + 1) * 4
+        ng, nc = B * n * V, B * n
+        per_step = inc(ng) + (inc(nc) if use_critic else 0)
+        seed, off = gen.initial_seed(), gen.get_offset()
+        gen.set_offset(off + timesteps * per_step)
+        if getattr(self, "_aten_dev", None) is None or self._aten_dev.device != device:
+            self._aten_dev = torch.zeros((2,), dtype=torch.int64, device=device)
+        wrap = lambda v: v - (1 << 64) if v >= (1 << 63) else v
+        self._aten_dev.copy_(torch.tensor([wrap(seed), off], dtype=torch.int64), non_blocking=False)
+        return dict(key=(B, stride(ng), stride(nc), per_step), stride_g=stride(ng), stride_c=stride(nc), inc_g=inc(ng), per_step=per_step)
+
+    def _generate_body(self, text_embeds, cond_images, *, fmap_size, temperature, topk_filter_thres, timesteps, cond_scale, b,
+                       use_critic=False, critic_noise_scale=1., score_all=False, aten=None):
         """The device-side work of generate(): no host synchronisation, no data-dependent host control flow."""
         tr = self.transformer
         device = text_embeds.device
@@ -544,21 +624,51 @@ class MaskGit(nn.Module):
         k_keep = math.ceil((1 - topk_filter_thres) * V)                        # muse_maskgit_pytorch.py:414
         sched = self.mask_schedule(n, timesteps)
         e = torch.empty((b * n, tr.dim), device=device, dtype=adt)
-        logits = torch.empty((b * max(sched), V), device=device, dtype=torch.float32)
         bn = b * n
+        rows_max = n if score_all else max(sched)
+        logits = torch.empty((b * rows_max, V), device=device, dtype=torch.float32)
+        all_pos = torch.arange(n, dtype=torch.int32, device=device).repeat(b, 1).contiguous() if score_all else None
+        sc_embed = torch.empty((bn, tr.dim), device=device, dtype=torch.float32) if self.self_cond else None
+        # token critic (muse_maskgit_pytorch.py:535-538, 590-600): a second stack over the freshly filled ids scores EVERY position
+        if use_critic:
+            if isinstance(self.token_critic, SelfCritic):      # the generator itself; only its conditional embed is used (:352-361)
+                cnet, cnb, cctx = tr, 1, ctx
+                whead, bhead = self.token_critic._head()
+                whead = whead.to(device)
+            else:
+                cnet, cnb = self.token_critic, nb
+                cctx = cnet._prepare_context(text_embeds, cond_ids, [False, True][:nb])
+                whead, bhead = cnet._packed()["whead"], 0.
+                assert whead is not None, "token_critic must have dim_out == 1"
+            gcrit = cnet._packed()["gf"]
         for step, (num_masked, steps_until_x0) in enumerate(zip(sched, reversed(range(timesteps)))):
             ops.remask(ids, scores, masked_pos, num_masked, self.mask_id)
-            x = tr._run_blocks(ids, ctx, nb)
-            R = b * num_masked
-            ops.final_embed(x[:bn], x[bn:2 * bn] if nb == 2 else None, P["gf"], masked_pos, e, b, n, num_masked, float(cond_scale))
+            x = tr._run_blocks(ids, ctx, nb, sc_embed if (self.self_cond and step > 0) else None)
+            if self.self_cond:                                                 # embed of the conditional forward, fed back next step (:574)
+                ops.layernorm(x[:bn], P["gf"], sc_embed)
+            # rows that are sampled: the masked ones; every position when already-decoded tokens may be re-masked by confidence
+            pos, rows_b = (all_pos, n) if score_all else (masked_pos, num_masked)
+            R = b * rows_b
+            ops.final_embed(x[:bn], x[bn:2 * bn] if nb == 2 else None, P["gf"], pos, e, b, n, rows_b, float(cond_scale))
             lg = logits[:R]
             ops.linear(e[:R], P["wlog"], lg)
             temp = temperature * (steps_until_x0 / timesteps)                  # annealed, muse_maskgit_pytorch.py:578
             u = None
             if self.sampler_noise_fn is not None:
                 u = self.sampler_noise_fn(step, (b, n, V)).to(device=device, dtype=torch.float32).contiguous()
-            ops.logits_sample(lg, masked_pos, ids, scores, num_masked, k_keep, float(temp), u=u, seed=0, seed_dev=self._seed_dev,
-                              step=step, row_offset=self.row_offset * n)
+            seed_dev = self._seed_dev if aten is None else self._aten_dev[0:1]
+            ops.logits_sample(lg, pos, ids, scores, rows_b, k_keep, float(temp), u=u, seed=0, seed_dev=seed_dev,
+                              step=step, row_offset=self.row_offset * n, only_masked_id=self.mask_id if score_all else None,
+                              aten=None if aten is None else (step * aten["per_step"], self._aten_dev[1:2], aten["stride_g"]))
+            if use_critic:
+                xc = cnet._run_blocks(ids, cctx, cnb)
+                uc = None
+                if self.sampler_noise_fn is not None:
+                    uc = self.sampler_noise_fn(step, (b, n)).to(device=device, dtype=torch.float32).contiguous()
+                ops.critic_score(xc[:bn], xc[bn:2 * bn] if cnb == 2 else None, gcrit, whead, float(bhead), float(cond_scale),
+                                 float(critic_noise_scale * (steps_until_x0 / timesteps)), scores, u=uc, seed=0, seed_dev=seed_dev,
+                                 step=step, row_offset=self.row_offset * n,
+                                 aten=None if aten is None else (step * aten["per_step"] + aten["inc_g"], self._aten_dev[1:2], aten["stride_c"]))
         ids = ids.view(b, fmap_size, fmap_size)
         images = self.vae.decode_from_ids(ids)
         return images, ids

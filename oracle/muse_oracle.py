@@ -143,8 +143,9 @@ def gumbel_from_uniform(u):
     return -lg(-lg(u))
 
 
-def sample_step(logits, ids, mask_id, temperature, u, topk_thres=0.9):
-    """One sampling tail: ref muse_maskgit_pytorch.py:576-609 (no token critic, can_remask_prev_masked=False).
+def sample_step(logits, ids, mask_id, temperature, u, topk_thres=0.9, can_remask_prev_masked=False):
+    """One sampling tail: ref muse_maskgit_pytorch.py:576-612 (no token critic).  can_remask_prev_masked=True keeps the
+    confidence of already-decoded positions instead of pinning it to -1e5 (:609-612), so they compete for re-masking.
     `u` is the U[0,1) tensor the reference would draw with zeros_like(logits).uniform_(0,1).
     Returns (new_ids, new_scores, pred_ids)."""
     filtered = top_k_filter(logits, topk_thres)
@@ -153,7 +154,8 @@ def sample_step(logits, ids, mask_id, temperature, u, topk_thres=0.9):
     new_ids = torch.where(is_mask, pred, ids)
     probs = logits.softmax(dim=-1)
     scores = 1 - probs.gather(2, pred[..., None])[..., 0]
-    scores = scores.masked_fill(~is_mask, -1e5)
+    if not can_remask_prev_masked:
+        scores = scores.masked_fill(~is_mask, -1e5)
     return new_ids, scores, pred
 
 
@@ -163,28 +165,55 @@ def remask(ids, scores, num_masked, mask_id):
     return ids.scatter(1, idx, mask_id)
 
 
+def critic_scores(critic, ids, text_embeds, cond_ids, cond_scale, u, noise_mul):
+    """Token-critic scoring branch, ref: muse_maskgit_pytorch.py:590-600.
+
+    critic = dict(kind="token", sd, cfg)                 -> TokenCritic.forward_with_cond_scale (dim_out = 1 head, :383-386)
+           | dict(kind="self", sd, cfg, w_pred, b_pred)  -> SelfCritic (:352-361): to_pred(embed of the COND forward); the CFG-combined
+                                                            logits it also computes are discarded.
+    No self_cond_embed is passed to the critic (zeros -> FeedForward(0) = 0).  u = the (b, n) uniform_ draw of `uniform(scores.shape)`."""
+    if critic["kind"] == "token":
+        logit, _ = forward_with_cond_scale(critic["sd"], critic["cfg"], ids, text_embeds, cond_ids, cond_scale)
+        s = logit[..., 0]
+    else:
+        _, embed = transformer_forward(critic["sd"], critic["cfg"], ids, text_embeds, cond_ids, False, None, True)
+        s = (embed @ critic["w_pred"].t() + critic["b_pred"])[..., 0]
+    return s + (u - 0.5) * noise_mul
+
+
 def generate_ids(sd, cfg, text_embeds, seq_len, mask_id, noise_fn, cond_ids=None, timesteps=18,
-                 cond_scale=3.0, temperature=1.0, topk_thres=0.9, trace=None, max_steps=None):
-    """ref: muse_maskgit_pytorch.py:507-613 (token loop of MaskGit.generate; self_cond / critic off).
+                 cond_scale=3.0, temperature=1.0, topk_thres=0.9, trace=None, max_steps=None,
+                 critic=None, critic_noise_scale=1.0, can_remask_prev_masked=False):
+    """ref: muse_maskgit_pytorch.py:507-613 (token loop of MaskGit.generate).
 
     noise_fn(step, shape) -> U[0,1) fp32 tensor, standing in for `zeros_like(t).uniform_(0, 1)`
-    (muse_maskgit_pytorch.py:407).  trace (list) receives per-step dicts for teacher-forced parity."""
+    (muse_maskgit_pytorch.py:407) with shape (b, n, V), and — when a critic is given — for `uniform(scores.shape)`
+    (:598) with shape (b, n), called in the reference's order (gumbel draw, then critic draw, every step).
+    cfg["self_cond"]: the cond forward's embed is fed back through self_cond_to_init_embed on the next step (:574, 325-328).
+    trace (list) receives per-step dicts for teacher-forced parity."""
     b = text_embeds.shape[0]
     ids = torch.full((b, seq_len), mask_id, dtype=torch.long)
     scores = torch.zeros((b, seq_len), dtype=torch.float32)
     sched = mask_schedule(seq_len, timesteps)
+    self_cond_embed = None
     for step, (num_masked, steps_until_x0) in enumerate(zip(sched, reversed(range(timesteps)))):
         if max_steps is not None and step >= max_steps:      # bounded CPU-baseline sample (bench.py): stop early
             break
         ids = remask(ids, scores, num_masked, mask_id)
-        logits, _ = forward_with_cond_scale(sd, cfg, ids, text_embeds, cond_ids, cond_scale)
+        logits, embed = forward_with_cond_scale(sd, cfg, ids, text_embeds, cond_ids, cond_scale, self_cond_embed)
+        if cfg.get("self_cond", False):
+            self_cond_embed = embed
         temp = temperature * (steps_until_x0 / timesteps)
         u = noise_fn(step, logits.shape)
         masked_in = ids
-        ids, scores, pred = sample_step(logits, ids, mask_id, temp, u, topk_thres)
+        ids, scores, pred = sample_step(logits, ids, mask_id, temp, u, topk_thres, can_remask_prev_masked)
+        if critic is not None:
+            uc = noise_fn(step, scores.shape)
+            scores = critic_scores(critic, ids, text_embeds, cond_ids, cond_scale, uc,
+                                   critic_noise_scale * (steps_until_x0 / timesteps))
         if trace is not None:
             trace.append(dict(ids_in=masked_in, logits=logits, u=u, temperature=temp, pred=pred,
-                              ids_out=ids, scores=scores, num_masked=num_masked))
+                              ids_out=ids, scores=scores, num_masked=num_masked, embed=embed))
     return ids
 
 

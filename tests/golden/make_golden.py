@@ -145,4 +145,55 @@ images = mg2.generate(texts=["a"] * 2, cond_images=cond, timesteps=8)
 mg2.vae.decode_from_ids = orig
 _, cond_ids, _ = mg2.cond_vae.encode(cond)
 save("gen_superres_small", images=images, ids=grabbed["ids"], cond_ids=cond_ids.long())
+
+# ------------------------------------------------------------------ G6-G8: generate()'s optional branches
+from muse_maskgit_pytorch import TokenCritic                        # noqa: E402
+
+
+def run_generate(mg_, T, seed, **kw):
+    torch.manual_seed(seed)
+    g = {}
+    orig_ = mg_.vae.decode_from_ids
+    mg_.vae.decode_from_ids = lambda ids_, _o=orig_, _g=g: (_g.__setitem__("ids", ids_.clone()), _o(ids_))[1]
+    images_ = mg_.generate(texts=["a"] * 3, timesteps=T, cond_scale=3., temperature=1., **kw)
+    mg_.vae.decode_from_ids = orig_
+    return images_, g["ids"]
+
+
+# G6: self-conditioning (muse_maskgit_pytorch.py:325-328, 574)
+tr_sc = MaskGitTransformer(num_tokens=1024, dim=128, seq_len=16, depth=2, dim_head=64, heads=2,
+                           t5_name="synth-128", flash=False, self_cond=True).eval()
+fill(tr_sc, shapes.transformer_shapes(1024, 128, 16, 2, heads=2, text_dim=128), seed=21)
+tr_sc.encode_text = lambda texts: te
+mg_sc = MaskGit(image_size=16, transformer=tr_sc, vae=vae_s).eval()
+images, ids = run_generate(mg_sc, 8, 779)
+save("gen_selfcond_small", images=images, ids=ids)
+
+# G7: separate token critic (muse_maskgit_pytorch.py:383-386, 590-600)
+critic = TokenCritic(num_tokens=1024, dim=128, seq_len=16, depth=1, dim_head=64, heads=2, t5_name="synth-128", flash=False).eval()
+fill(critic, shapes.transformer_shapes(1024, 128, 16, 1, heads=2, text_dim=128, add_mask_id=False, dim_out=1), seed=22)
+critic.encode_text = lambda texts: te
+mg_tc = MaskGit(image_size=16, transformer=tr, vae=vae_s, token_critic=critic).eval()
+tr.encode_text = lambda texts: te
+images, ids = run_generate(mg_tc, 8, 780, critic_noise_scale=0.7)
+save("gen_critic_small", images=images, ids=ids)
+images, ids = run_generate(mg_tc, 8, 780, force_not_use_token_critic=True)
+save("gen_critic_forced_off_small", images=images, ids=ids)
+
+# G8: self token critic on a self-conditioned transformer (muse_maskgit_pytorch.py:352-361, 475-476)
+mg_self = MaskGit(image_size=16, transformer=tr_sc, vae=vae_s, self_token_critic=True).eval()
+wp = torch.from_numpy(synth.normal("g8.to_pred.weight", (1, 128), 23)) * 0.2
+bp = torch.from_numpy(synth.normal("g8.to_pred.bias", (1,), 23)) * 0.2
+mg_self.token_critic.to_pred.weight.copy_(wp)
+mg_self.token_critic.to_pred.bias.copy_(bp)
+keys = sorted(k for k in mg_self.state_dict() if k.startswith("token_critic.") and not k.startswith("token_critic.net."))
+assert keys == ["token_critic.to_pred.bias", "token_critic.to_pred.weight"], keys
+assert "token_critic.net.to_logits.weight" in mg_self.state_dict()
+images, ids = run_generate(mg_self, 8, 781)
+save("gen_selfcritic_small", images=images, ids=ids, w_pred=wp, b_pred=bp)
+
+# G9: can_remask_prev_masked=True (muse_maskgit_pytorch.py:609-612; requires no_mask_token_prob > 0)
+mg_rm = MaskGit(image_size=16, transformer=tr, vae=vae_s, no_mask_token_prob=0.1).eval()
+images, ids = run_generate(mg_rm, 8, 782, can_remask_prev_masked=True)
+save("gen_remask_prev_small", images=images, ids=ids)
 print("done")

@@ -525,3 +525,26 @@ def test_linear_residual_with_fused_layernorm(N):
     ok, msg = close(xn, lref, 2e-2, 1e-2)
     assert ok, "ln_out: " + msg
     assert float(stats.abs().max()) == 0.
+
+
+@pytest.mark.parametrize("cfg_branch", [False, True])
+def test_critic_score(cfg_branch):
+    """mmg_critic_score vs torch: final LayerNorm + 1-wide head + CFG + annealed noise (ref: muse_maskgit_pytorch.py:590-600)."""
+    from oracle import philox
+    torch.manual_seed(3)
+    rows, dim = 37, 128
+    xc, xn = torch.randn(rows, dim) * 2 + 0.3, torch.randn(rows, dim)
+    g, w = torch.rand(dim) + 0.5, torch.randn(dim) * 0.1
+    u = torch.rand(rows)
+    head = lambda x: torch.nn.functional.layer_norm(x, (dim,), g, None, 1e-5) @ w + 0.25
+    want = head(xc)
+    if cfg_branch:
+        want = head(xn) + (want - head(xn)) * 3.0
+    sc = torch.zeros(rows, device="cuda")
+    ops.critic_score(xc.cuda(), xn.cuda() if cfg_branch else None, g.cuda(), w.cuda(), 0.25, 3.0, 0.6, sc, u=u.cuda())
+    assert (sc.cpu() - (want + (u - 0.5) * 0.6)).abs().max() < 1e-5
+    # Philox stream: counter (0xFFFFFFFF, step, global row), key = seed  -> same numbers as oracle/philox.py
+    seed_dev = torch.tensor([11], dtype=torch.int64, device="cuda")
+    ops.critic_score(xc.cuda(), xn.cuda() if cfg_branch else None, g.cuda(), w.cuda(), 0.25, 3.0, 0.6, sc, seed=1, seed_dev=seed_dev, step=4, row_offset=100)
+    up = torch.tensor([float(philox.uniform_at(12, 4, 100 + r, 0xFFFFFFFF)) for r in range(rows)])
+    assert (sc.cpu() - (want + (up - 0.5) * 0.6)).abs().max() < 1e-5

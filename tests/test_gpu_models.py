@@ -230,6 +230,80 @@ def test_generate_bf16_philox_shapes_and_determinism():
     assert torch.equal(idc, ida[1:])
 
 
+def make_branch_maskgit(name, precision):
+    """MaskGit variants of the optional-branch fixtures G6-G9 (tests/golden/make_golden.py)."""
+    m = M()
+    vae = small_vae(precision)
+    tr_sc = lambda: load(m.MaskGitTransformer(num_tokens=1024, dim=128, seq_len=16, depth=2, heads=2, t5_name="synth-128",
+                                              self_cond=True, precision=precision),
+                         util.transformer_sd(1024, 128, 16, 2, 2, seed=21, text_dim=128))
+    if name == "gen_selfcond_small":
+        return m.MaskGit(image_size=16, transformer=tr_sc(), vae=vae).cuda(), {}, 779
+    if name in ("gen_critic_small", "gen_critic_forced_off_small"):
+        critic = load(m.TokenCritic(num_tokens=1024, dim=128, seq_len=16, depth=1, heads=2, t5_name="synth-128", precision=precision),
+                      util.critic_sd(1024, 128, 16, 1, 2, seed=22, text_dim=128))
+        mg = m.MaskGit(image_size=16, transformer=small_transformer(precision), vae=vae, token_critic=critic).cuda()
+        kw = dict(critic_noise_scale=0.7) if name == "gen_critic_small" else dict(force_not_use_token_critic=True)
+        return mg, kw, 780
+    if name == "gen_remask_prev_small":
+        mg = m.MaskGit(image_size=16, transformer=small_transformer(precision), vae=vae, no_mask_token_prob=0.1).cuda()
+        return mg, dict(can_remask_prev_masked=True), 782
+    mg = m.MaskGit(image_size=16, transformer=tr_sc(), vae=vae, self_token_critic=True)
+    w, b = util.self_critic_head()
+    mg.token_critic.to_pred.weight.data.copy_(w); mg.token_critic.to_pred.bias.data.copy_(b)
+    assert "token_critic.to_pred.weight" in mg.state_dict() and "token_critic.net.to_logits.weight" in mg.state_dict()
+    return mg.cuda(), {}, 781
+
+
+BRANCHES = ["gen_selfcond_small", "gen_critic_small", "gen_critic_forced_off_small", "gen_selfcritic_small", "gen_remask_prev_small"]
+
+
+@pytest.mark.parametrize("name", BRANCHES)
+def test_generate_optional_branches_fp32_token_identical_to_reference(name):
+    """self-conditioning feedback, TokenCritic / SelfCritic scoring and can_remask_prev_masked: token ids
+    bit-identical to the unmodified reference with its noise stream injected (gumbel draw, then critic draw, per step)."""
+    g = util.golden(name)
+    mg, kw, seed = make_branch_maskgit(name, "fp32")
+    te = util.text_embeds("g4.te", 3, 8, 128, 14)
+    mg.transformer.encode_text = lambda texts: te
+    mg.sampler_noise_fn = util.torch_noise_fn(seed)
+    images, ids = mg.generate(texts=["a"] * 3, timesteps=8, return_ids=True, **kw)
+    assert torch.equal(ids.cpu(), g["ids"]), (ids.cpu() != g["ids"]).sum()
+    assert (images.cpu() - g["images"]).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("name", ["gen_selfcond_small", "gen_critic_small", "gen_selfcritic_small", "gen_remask_prev_small"])
+def test_generate_optional_branches_bf16_graph_equals_eager(name):
+    """bf16 + in-kernel Philox: the CUDA-graph replay and the eager launch sequence produce the same tokens, and a batch shard
+    generated alone (row_offset) reproduces its rows (the critic noise is keyed by global position too)."""
+    mg, kw, _ = make_branch_maskgit(name, "bf16")
+    te = util.text_embeds("g4.te", 3, 8, 128, 14).cuda()
+    mg.transformer.encode_text = lambda texts: te[:len(texts)]
+    mg.sampler_seed = 5
+    a, ida = mg.generate(texts=["a"] * 3, timesteps=8, return_ids=True, **kw)
+    a2, ida2 = mg.generate(texts=["a"] * 3, timesteps=8, return_ids=True, **kw)        # replay
+    mg.use_cuda_graph = False
+    b_, idb = mg.generate(texts=["a"] * 3, timesteps=8, return_ids=True, **kw)
+    assert torch.equal(ida, idb) and torch.equal(ida, ida2) and torch.equal(a, b_) and torch.isfinite(a).all()
+    assert int(ida.min()) >= 0 and int(ida.max()) < 1024
+    mg.row_offset = 1
+    mg.transformer.encode_text = lambda texts: te[1:1 + len(texts)]
+    _, idc = mg.generate(texts=["a"] * 2, timesteps=8, return_ids=True, **kw)
+    assert torch.equal(idc, ida[1:])
+
+
+def test_token_critic_forward_vs_oracle():
+    """TokenCritic.forward_with_cond_scale (dim_out = 1 head) at the class boundary."""
+    m = M()
+    sd = util.critic_sd(1024, 128, 16, 1, 2, seed=22, text_dim=128)
+    critic = load(m.TokenCritic(num_tokens=1024, dim=128, seq_len=16, depth=1, heads=2, t5_name="synth-128", precision="fp32"), sd)
+    te = util.text_embeds("g4.te", 3, 8, 128, 14)
+    ids = torch.from_numpy((synth.uniform("crit.ids", (3, 16), 3) * 1024).astype(np.int64))
+    want, _ = O.forward_with_cond_scale(sd, dict(heads=2, depth=1), ids, te, None, 3.0)
+    got = critic.forward_with_cond_scale(ids.cuda(), text_embeds=te.cuda(), cond_scale=3.)
+    assert got.shape == (3, 16, 1) and (got.cpu() - want).abs().max() < 2e-4
+
+
 def test_muse_cascade_runs_on_device():
     """Muse(base, superres): base generate -> superres generate conditioned on the low-res images (kept on the device)."""
     m = M()

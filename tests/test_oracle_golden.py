@@ -99,6 +99,39 @@ def test_generate_superres_small():
     assert torch.allclose(images, g["images"], atol=1e-5)
 
 
+def _branch_case(name):
+    """(golden, oracle kwargs, torch seed) of the optional-branch fixtures G6-G8 (make_golden.py)."""
+    cfg_sc = dict(CFG, self_cond=True)
+    if name == "gen_selfcond_small":
+        return util.transformer_sd(1024, 128, 16, 2, 2, seed=21, text_dim=128), cfg_sc, {}, 779
+    if name == "gen_critic_small":
+        crit = dict(kind="token", sd=util.critic_sd(1024, 128, 16, 1, 2, seed=22, text_dim=128), cfg=dict(heads=2, depth=1))
+        return util.transformer_sd(1024, 128, 16, 2, 2, seed=13, text_dim=128), CFG, dict(critic=crit, critic_noise_scale=0.7), 780
+    if name == "gen_critic_forced_off_small":
+        return util.transformer_sd(1024, 128, 16, 2, 2, seed=13, text_dim=128), CFG, {}, 780
+    if name == "gen_remask_prev_small":
+        return util.transformer_sd(1024, 128, 16, 2, 2, seed=13, text_dim=128), CFG, dict(can_remask_prev_masked=True), 782
+    sd = util.transformer_sd(1024, 128, 16, 2, 2, seed=21, text_dim=128)
+    w, b = util.self_critic_head()
+    return sd, cfg_sc, dict(critic=dict(kind="self", sd=sd, cfg=cfg_sc, w_pred=w, b_pred=b)), 781
+
+
+@pytest.mark.parametrize("name", ["gen_selfcond_small", "gen_critic_small", "gen_critic_forced_off_small", "gen_selfcritic_small",
+                                  "gen_remask_prev_small"])
+def test_generate_optional_branches(name):
+    """self-conditioning feedback, TokenCritic and SelfCritic scoring (SURVEY.md 8f #3) against the unmodified reference."""
+    g = util.golden(name)
+    sd, cfg, kw, seed = _branch_case(name)
+    vsd = util.vae_sd(16, 2, 1024, seed=12)
+    te = util.text_embeds("g4.te", 3, 8, 128, 14)
+    images, ids = O.generate(sd, cfg, vsd, 10, te, 4, util.torch_noise_fn(seed), timesteps=8, **kw)
+    assert torch.equal(ids.view(3, 4, 4), g["ids"])
+    assert torch.allclose(images, g["images"], atol=1e-5)
+    if kw or cfg.get("self_cond"):       # the fixture is discriminative: dropping the branch changes the tokens
+        plain, _ = O.generate_ids(sd, dict(cfg, self_cond=False), te, 16, 1024, util.torch_noise_fn(seed), timesteps=8), None
+        assert not torch.equal(plain.view(3, 4, 4), g["ids"])
+
+
 def test_philox_known_answer():
     """Random123 known-answer vector for Philox4x32-10 (zero counter, zero key -> 6627e8d5 ...): pins oracle/philox.py,
     against which the in-kernel generator is tested on the GPU."""

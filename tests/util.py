@@ -24,6 +24,18 @@ def transformer_sd(num_tokens, dim, seq_len, depth, heads, seed, text_dim=None, 
     return sd
 
 
+def critic_sd(num_tokens, dim, seq_len, depth, heads, seed, text_dim=None):
+    """TokenCritic: no mask row in token_emb, dim_out = 1 (ref: muse_maskgit_pytorch.py:383-386)."""
+    return sd_from_table(shapes.transformer_shapes(num_tokens, dim, seq_len, depth, heads=heads, text_dim=text_dim,
+                                                   add_mask_id=False, dim_out=1), seed)
+
+
+def self_critic_head(seed=23, dim=128):
+    w = torch.from_numpy(synth.normal("g8.to_pred.weight", (1, dim), seed)) * 0.2
+    b = torch.from_numpy(synth.normal("g8.to_pred.bias", (1,), seed)) * 0.2
+    return w, b
+
+
 def vae_sd(dim, layers, codebook_size, seed):
     return sd_from_table(shapes.vae_shapes(dim, layers=layers, codebook_size=codebook_size), seed)
 
