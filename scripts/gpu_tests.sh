@@ -17,10 +17,7 @@ runall() { # same but without -x
   echo "exit $?: $(tail -1 $OUT/$name.log)" | tee -a $OUT/summary.txt
 }
 : > $OUT/summary.txt
-runall k_fp32 600 tests/test_gpu_kernels.py -k "fp32 or remask or sample or vq or embed or layernorm"
-runall k_bf16_gemm 300 tests/test_gpu_kernels.py -k "bf16 and linear"
-runall k_bf16_attn 300 tests/test_gpu_kernels.py -k "bf16 and attention"
-runall k_bf16_conv 300 tests/test_gpu_kernels.py -k "(bf16 and (conv or groupnorm)) or fused_rgb"
-runall m_fp32 600 tests/test_gpu_models.py -k "fp32 or explicit"
-runall m_bf16 600 tests/test_gpu_models.py -k "bf16"
+runall kernels 900 tests/test_gpu_kernels.py
+runall models 900 tests/test_gpu_models.py
+runall aten_rng 600 tests/test_gpu_aten_rng.py
 cat $OUT/summary.txt

@@ -541,10 +541,10 @@ def test_critic_score(cfg_branch):
     if cfg_branch:
         want = head(xn) + (want - head(xn)) * 3.0
     sc = torch.zeros(rows, device="cuda")
-    ops.critic_score(xc.cuda(), xn.cuda() if cfg_branch else None, g.cuda(), w.cuda(), 0.25, 3.0, 0.6, sc, u=u.cuda())
+    ops().critic_score(xc.cuda(), xn.cuda() if cfg_branch else None, g.cuda(), w.cuda(), 0.25, 3.0, 0.6, sc, u=u.cuda())
     assert (sc.cpu() - (want + (u - 0.5) * 0.6)).abs().max() < 1e-5
     # Philox stream: counter (0xFFFFFFFF, step, global row), key = seed  -> same numbers as oracle/philox.py
     seed_dev = torch.tensor([11], dtype=torch.int64, device="cuda")
-    ops.critic_score(xc.cuda(), xn.cuda() if cfg_branch else None, g.cuda(), w.cuda(), 0.25, 3.0, 0.6, sc, seed=1, seed_dev=seed_dev, step=4, row_offset=100)
+    ops().critic_score(xc.cuda(), xn.cuda() if cfg_branch else None, g.cuda(), w.cuda(), 0.25, 3.0, 0.6, sc, seed=1, seed_dev=seed_dev, step=4, row_offset=100)
     up = torch.tensor([float(philox.uniform_at(12, 4, 100 + r, 0xFFFFFFFF)) for r in range(rows)])
     assert (sc.cpu() - (want + (up - 0.5) * 0.6)).abs().max() < 1e-5
