@@ -1,6 +1,7 @@
 // tcgen05 attention for dh = 64 (bf16 operands, fp32 softmax statistics).
 //
-// One CTA = one (batch, head, 128-query tile).  Keys are walked in nb blocks of KB (<= 256, multiple of 32) keys, twice:
+// One CTA = one (batch, head, 128-query tile).  Keys are walked in nb blocks of KB (<= 256, multiple of 32) keys (the last block
+// may be shorter: KB_tail), twice (or once, see single_pass):
 //   pass A:  S = Q K^T (tcgen05.mma, M=128, N=KB, 4 k-steps) -> TMEM -> per-row running max        (no P, no V traffic)
 //   pass B:  S again -> p = exp2((s - max) * scale*log2e) in registers (masked / out-of-range keys -> 0), row sums in fp32,
 //            P (bf16) written to shared memory in the K-major SWIZZLE_128B operand layout, O += P V (tcgen05.mma, M=128,
@@ -21,7 +22,7 @@ struct alignas(64) AttnTcParams {
   CUtensorMap tma_q, tma_k, tma_v;
   const uint8_t* key_mask;
   bf16* out;
-  int heads, Tq, Tk, Tk_alloc, nb, KB, kv_shared;
+  int heads, Tq, Tk, Tk_alloc, nb, KB, KB_tail, kv_shared;   // nb key blocks: nb-1 of KB keys, the last of KB_tail (<= KB, multiple of 32)
   int64_t ldo;
   float scale_log2e;
   float smax;              // > 0: caller-guaranteed bound on |q.k| -> single-pass softmax with a fixed reference maximum
@@ -69,16 +70,18 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
   if (warp == 4) {
     if (elect_one()) {
       const uint32_t idesc_s = idesc_bf16_f32(128, (uint32_t)KB, false, false);
+      const uint32_t idesc_s_tail = idesc_bf16_f32(128, (uint32_t)p.KB_tail, false, false);
       const uint32_t idesc_o = idesc_bf16_f32(128, 64, false, true);          // B (= V) is MN-major
       const uint64_t qdesc = smem_desc_kmajor_sw128(smem_u32(sQ));
       const uint64_t kdesc = smem_desc_kmajor_sw128(smem_u32(sK));
-      auto issue_s = [&]() {
+      auto issue_s = [&](int blk) {
+        const uint32_t id = blk == p.nb - 1 ? idesc_s_tail : idesc_s;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), id, k ? 1u : 0u);
         umma_commit(bar_s);
       };
       auto issue_pv = [&](int blk) {
-        const int ksteps = KB / 16;
+        const int ksteps = (blk == p.nb - 1 ? p.KB_tail : KB) / 16;
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint32_t pa = smem_u32(sP) + (ks >> 2) * 16384 + (ks & 3) * 32;
           umma_f16(tO, smem_desc_kmajor_sw128(pa), smem_desc_mnmajor_sw128(smem_u32(sV) + ks * 2048, 1024), idesc_o, (blk | ks) ? 1u : 0u);
@@ -97,7 +100,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
         tma_load_2d(sV, &p.tma_v, bar_kv, 0, krow0);
         mbar_wait(bar_q, 0);
         tc_fence_after();
-        issue_s();
+        issue_s(0);
         for (int blk = 0; blk < p.nb; ++blk) {
           const bool more = blk + 1 < p.nb;
           mbar_wait(bar_s, ph_s); ph_s ^= 1;                     // S(blk) retired: K smem reusable
@@ -106,7 +109,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
           mbar_wait(bar_kv, ph_v); ph_v ^= 1;                    // V(blk) landed
           tc_fence_after();
           issue_pv(blk);
-          if (more) { mbar_wait(bar_k, ph_k); ph_k ^= 1; tc_fence_after(); issue_s(); }
+          if (more) { mbar_wait(bar_k, ph_k); ph_k ^= 1; tc_fence_after(); issue_s(blk + 1); }
           mbar_wait(bar_pv, ph_pv); ph_pv ^= 1;                  // P / V smem reusable; after the last block O is final
           if (more) { mbar_expect_tx(bar_kv, kv_bytes); tma_load_2d(sV, &p.tma_v, bar_kv, 0, krow0 + (blk + 1) * KB); }
         }
@@ -123,22 +126,13 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
           if (pass == 1) tma_load_2d(sV, &p.tma_v, bar_kv, 0, krow);
           mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
           tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
-          umma_commit(bar_s);
+          issue_s(blk);
           if (pass == 0) {
             mbar_wait(bar_sdone, ph_sdone); ph_sdone ^= 1;      // softmax warps consumed S; K smem is free (MMA retired before S was readable)
           } else {
             mbar_wait(bar_p, ph_p); ph_p ^= 1;                  // P staged in smem (and S consumed)
             tc_fence_after();
-            const int ksteps = KB / 16;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t pa = smem_u32(sP) + (ks >> 2) * 16384 + (ks & 3) * 32;
-              const uint64_t pdesc = smem_desc_kmajor_sw128(pa);
-              const uint64_t vdesc = smem_desc_mnmajor_sw128(smem_u32(sV) + ks * 2048, 1024);
-              umma_f16(tO, pdesc, vdesc, idesc_o, (blk | ks) ? 1u : 0u);
-            }
-            umma_commit(bar_pv);
+            issue_pv(blk);
             mbar_wait(bar_pv, ph_pv); ph_pv ^= 1;               // K/V/P smem free again; on the last block: O complete
           }
         }
@@ -160,7 +154,8 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
       for (int blk = 0; blk < p.nb; ++blk) {
         mbar_wait(bar_s, ph_s); ph_s ^= 1;
         tc_fence_after();
-        for (int c = 0; c < KB; c += 32) {
+        const int kb_cur = blk == p.nb - 1 ? p.KB_tail : KB;
+        for (int c = 0; c < kb_cur; c += 32) {
           float s[32];
           tmem_ld_32x32b_x32(tS + lane_base + c, s);
           tmem_ld_wait();
@@ -180,7 +175,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
               // fast path (self-attention, chunk fully inside the key range): no per-key liveness tests
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
-                const float p0 = exp2f(fmaf(s[i], p.scale_log2e, -mneg)), p1 = exp2f(fmaf(s[i + 1], p.scale_log2e, -mneg));
+                const float p0 = ex2_fast(fmaf(s[i], p.scale_log2e, -mneg)), p1 = ex2_fast(fmaf(s[i + 1], p.scale_log2e, -mneg));
                 __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
                 packed[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
                 const float2 pr = __bfloat1622float2(t);
@@ -194,7 +189,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
               for (int e = 0; e < 2; ++e) {
                 const int j = j0 + i + e;
                 const bool live = j < p.Tk && (j == 0 || !km || km[j - 1]);
-                pv[e] = live ? exp2f(fmaf(s[i + e], p.scale_log2e, -mneg)) : 0.f;
+                pv[e] = live ? ex2_fast(fmaf(s[i + e], p.scale_log2e, -mneg)) : 0.f;
               }
               __nv_bfloat162 t = __floats2bfloat162_rn(pv[0], pv[1]);
               packed[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
@@ -256,12 +251,17 @@ inline bool attention_tc_supported(const mmg_attention_args* a) {
   return al(a->q) && al(a->k) && al(a->v) && al(a->out) && (a->ldo % 8 == 0) && a->Tk <= 4096;
 }
 
-inline void attn_blocks(int Tk, int* nb, int* KB) {
-  *nb = (Tk + 255) / 256;
-  int kb = (Tk + *nb - 1) / *nb;
-  kb = (kb + 31) / 32 * 32;
-  if (kb < 32) kb = 32;
+// Key blocking: nb-1 blocks of KB keys and a last block of KB_tail keys (multiple of 32).  KB = 64 keeps S (64 fp32 columns) + O (64)
+// inside a 128-column TMEM allocation and ~50 KB of shared memory, so four CTAs share an SM and hide each other's
+// MMA -> softmax -> MMA round trips; long sequences use 128-key blocks (fewer round trips per CTA, two CTAs per SM).
+inline void attn_blocks(int Tk, int* nb, int* KB, int* KB_tail) {
+  static const int forced = [] { const char* e = getenv("MMG_ATTN_KB"); return e ? atoi(e) : 0; }();
+  int kb = forced ? forced : (Tk <= 640 ? 64 : 128);
+  if (kb != 32 && kb != 64 && kb != 128 && kb != 160 && kb != 256) kb = 64;
+  const int full = Tk / kb, rem = Tk - full * kb;
   *KB = kb;
+  if (rem == 0) { *nb = full; *KB_tail = kb; }
+  else { *nb = full + 1; *KB_tail = (rem + 31) / 32 * 32; }
 }
 
 int attention_tc_launch(const mmg_attention_args* a, cudaStream_t st);
