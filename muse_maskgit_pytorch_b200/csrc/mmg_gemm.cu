@@ -23,11 +23,11 @@ template <int BN>
 static int launch_tc_lnf(const TcGemmParams& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES); });
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES_LNF); });
   if (attr_err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(tc_gemm_lnf<%d>): %s", BN, cudaGetErrorString(attr_err));
   const int pairs = p.num_m_tiles < num_sms() / 2 ? p.num_m_tiles : num_sms() / 2;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<BN>::SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<BN>::SMEM_BYTES_LNF; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
@@ -35,6 +35,48 @@ static int launch_tc_lnf(const TcGemmParams& p, cudaStream_t st) {
   MMG_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, true>, p));
   MMG_LAUNCHED();
   return MMG_OK;
+}
+
+// CTA-pair variant (cta_group::2): clusters of two CTAs, one 256 x BN tile per pair and step
+template <int BN>
+static int launch_tc_pair(const TcGemmParams& p, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  static int max_clusters = 0;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::PAIR_SMEM_BYTES);
+    if (attr_err != cudaSuccess) return;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (num_sms() / 2)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<BN>::PAIR_SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr_err = cudaOccupancyMaxActiveClusters(&max_clusters, tc_gemm_kernel<BN, false, true>, &cfg);
+  });
+  if (attr_err != cudaSuccess || max_clusters < 1) return fail(MMG_ECUDA, "tc_gemm pair<%d> setup: %s (clusters %d)", BN, cudaGetErrorString(attr_err), max_clusters);
+  const int tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<BN>::PAIR_SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  MMG_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, false, true>, p));
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
+// CTA pairs (cta_group::2) cut the L2->SM operand traffic by a third and deepen the ring to six stages: -18 % on a tile with a long
+// K loop (8192^3: 79 650 -> 65 570 cycles per tile), which is where the operand feed is the limiter (the 3x3 convolutions of the
+// VAE, K = 9 * Cin).  The K = 512 transformer GEMMs are bound by their epilogues and get slower in lock-step pairs, so they stay on
+// single CTAs.  MMG_GEMM_PAIR = 0 / 1 forces the choice for A/B measurements.
+static bool use_pair(const TcGemmParams& p, int bn) {
+  static const int forced = [] { const char* e = getenv("MMG_GEMM_PAIR"); return e ? atoi(e) : -1; }();
+  if (bn != 256 || forced == 0 || p.num_m_tiles < 2) return false;
+  if (forced == 1) return true;
+  return p.mode == 1 && p.epi.kind != MMG_EPI_CONVT && p.epi.kind != MMG_EPI_CONVT_RGB && p.num_kb >= 64 &&
+         ((p.num_m_tiles + 1) / 2) * p.num_n_tiles >= 64;
 }
 
 static int pick_bn(int64_t M_tiles, int64_t N, int epilogue) {
@@ -46,9 +88,11 @@ static int pick_bn(int64_t M_tiles, int64_t N, int epilogue) {
 }
 
 static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_t K, int64_t ldw, cudaStream_t st) {
-  uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; uint64_t str[1] = {(uint64_t)ldw * 2}; uint32_t box[2] = {TC_BK, (uint32_t)bn};
-  int rc = make_tmap_bf16(&p.tma_b, w, 2, dims, str, box); if (rc) return rc;
   p.num_n_tiles = (int)((N + bn - 1) / bn);
+  const bool pair = use_pair(p, bn);
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; uint64_t str[1] = {(uint64_t)ldw * 2}; uint32_t box[2] = {TC_BK, (uint32_t)(pair ? bn / 2 : bn)};
+  int rc = make_tmap_bf16(&p.tma_b, w, 2, dims, str, box); if (rc) return rc;
+  if (pair) return launch_tc_pair<256>(p, st);
   switch (bn) {
     case 64: return launch_tc<64>(p, st);
     case 128: return launch_tc<128>(p, st);
@@ -286,3 +330,9 @@ extern "C" int mmg_conv_transpose2d(const mmg_conv_transpose2d_args* a, void* st
   }
   return MMG_OK;
 }
+
+#ifdef MMG_GEMM_TRACE
+extern "C" int mmg_trace_read(void* dst, size_t bytes) {
+  return (int)cudaMemcpyFromSymbol(dst, mmg::g_gemm_trace, bytes < sizeof(mmg::g_gemm_trace) ? bytes : sizeof(mmg::g_gemm_trace));
+}
+#endif

@@ -37,37 +37,61 @@ struct alignas(64) TcGemmParams {
   Epilogue epi;
 };
 
+// -DMMG_GEMM_TRACE (scripts/trace_gemm.py only): per-CTA, per-tile clock64() stamps of the three roles, to see which of
+// TMA / MMA issue / epilogue a tile period is made of.  Compiles to nothing in the product build.
+#ifdef MMG_GEMM_TRACE
+__device__ long long g_gemm_trace[160 * 32 * 10];
+#define MMG_TR(slot, val) do { if (tile_i < 32) g_gemm_trace[((size_t)blockIdx.x * 32 + tile_i) * 10 + (slot)] = (val); } while (0)
+#define MMG_CLK() clock64()
+#else
+#define MMG_TR(slot, val) do {} while (0)
+#define MMG_CLK() 0ll
+#endif
+
 template <int BN> struct TcCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = TC_EPI_WARPS * 4096;    // one 32-row x 128-byte transpose tile per epilogue warp (mmg_epilogue.cuh)
+  static constexpr int SMEM_BYTES_LNF = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = SMEM_BYTES_LNF + STAGING_BYTES;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  // CTA pair (cta_group::2, M = 256 over two SMs): each CTA stages its own 128 rows of A and HALF of the W tile, so a k-block costs
+  // 32 KB of L2->SM traffic per SM instead of 48 KB and six stages fit where four did
+  static constexpr int PAIR_STAGES = 6;
+  static constexpr int PAIR_STAGE_BYTES = A_BYTES + B_BYTES / 2;
+  static constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256 + STAGING_BYTES;
 };
 
 // LNF: the epilogue additionally emits LayerNorm(out row) as bf16 (see mmg_epilogue_args::ln_out).  Launched as clusters of two
 // CTAs that own the two column halves (N == 2 * BN) of the same 128 rows; per-row (sum, sumsq) partials cross through DSMEM.
-template <int BN, bool LNF = false>
+// PAIR: launched as clusters of two CTAs that form one tcgen05 CTA pair: a 256 x BN output tile per pair, the leader (rank 0) issues
+// the MMAs for both SMs, TMA completions of both CTAs are counted on the leader's barriers, MMA commits are multicast to both.
+template <int BN, bool LNF = false, bool PAIR = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   using namespace sm100;
   using Cfg = TcCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  static_assert(!(LNF && PAIR), "LayerNorm fusion and CTA pairs both claim the cluster");
+  constexpr int STAGES = PAIR ? Cfg::PAIR_STAGES : Cfg::STAGES;
+  constexpr int STAGE_BYTES = PAIR ? Cfg::PAIR_STAGE_BYTES : Cfg::STAGE_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = LNF ? p.num_m_tiles : p.num_m_tiles * p.num_n_tiles;      // LNF: this CTA walks m-blocks, n-block = cluster rank
-  const int tile0 = LNF ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_step = LNF ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_pm = PAIR ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;             // PAIR: tiles are 256 rows tall, CTA `rank` owns rows [128 * rank, +128)
+  const int num_tiles = LNF ? p.num_m_tiles : num_pm * p.num_n_tiles;             // LNF: this CTA walks m-blocks, n-block = cluster rank
+  const int tile0 = (LNF || PAIR) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = (LNF || PAIR) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int my_rank = LNF ? (int)(blockIdx.x & 1) : 0;
+  const int pair_rank = PAIR ? (int)cluster_ctarank() : 0;
   __shared__ float s_part[LNF ? 2 : 1][2][LNF ? 128 : 1][2][2];                    // [buffer][cta rank][row][column half][sum, sumsq]
   __shared__ uint64_t s_bar_stats;
   __shared__ float s_scale[128];               // QKV epilogue: q_scale | k_scale staged once per CTA
@@ -80,16 +104,16 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     prefetch_tmap(&p.tma_b);
     prefetch_tmap(&p.tma_a[0]);
     for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, TC_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
     if (LNF) mbar_init(&s_bar_stats, 2 * TC_EPI_WARPS * 32);      // every epilogue thread of both CTAs arrives once per tile
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  if (warp == 1) { if (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr); else tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  if (LNF) cluster_sync_all();                  // the peer's barrier must exist before the first remote arrive
+  if (LNF || PAIR) cluster_sync_all();          // the peer's barriers must exist before the first remote arrive / TMA completion
   pdl_wait();                                   // everything above overlapped the previous kernel's tail
   pdl_trigger();
 
@@ -99,17 +123,34 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = LNF ? tile : tile % p.num_m_tiles, n_blk = LNF ? my_rank : tile / p.num_m_tiles;
+      [[maybe_unused]] int tile_i = 0;
+      const uint32_t full0 = PAIR ? mapa_shared(smem_u32(full_bar), 0) : 0u;      // the leader's full barriers, as seen from this CTA
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_i) {
+        const int m_blk = LNF ? tile : PAIR ? 2 * (tile % num_pm) + pair_rank : tile % p.num_m_tiles;
+        const int n_blk = LNF ? my_rank : tile / num_pm;
+        [[maybe_unused]] long long w_empty = 0;
         int x0 = 0, y0 = 0, b0 = 0;
         if (p.mode == 1) {
           const int xt = m_blk % p.tiles_x, yt = (m_blk / p.tiles_x) % p.tiles_y, bt = m_blk / (p.tiles_x * p.tiles_y);
           x0 = xt * p.TW; y0 = yt * p.TH; b0 = bt * p.TB;
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(empty_bar + stage, phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          { [[maybe_unused]] const long long t0 = MMG_CLK(); mbar_wait(empty_bar + stage, phase ^ 1); w_empty += MMG_CLK() - t0; }
+          uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          if (PAIR) {
+            // both CTAs' bytes complete on the leader's barrier, which alone arms it (a completion that lands before the leader
+            // armed the phase only drives the transaction count negative for a moment)
+            const uint32_t fb = full0 + (uint32_t)stage * 8u;
+            if (pair_rank == 0) mbar_expect_tx(full_bar + stage, 2 * STAGE_BYTES);
+            if (p.mode == 0) {
+              tma_load_2d_pair(sa, &p.tma_a[0], fb, kb * TC_BK, m_blk * TC_BM);
+            } else {
+              const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+              tma_load_4d_pair(sa, &p.tma_a[p.tap_map[tap]], fb, cc * TC_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
+            }
+            tma_load_2d_pair(sb, &p.tma_b, fb, kb * TC_BK, n_blk * BN + pair_rank * (BN / 2));
+          } else {
           mbar_expect_tx(full_bar + stage, Cfg::STAGE_BYTES);
           if (p.mode == 0) {
             tma_load_2d(sa, &p.tma_a[0], full_bar + stage, kb * TC_BK, m_blk * TC_BM);
@@ -118,35 +159,51 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
             tma_load_4d(sa, &p.tma_a[p.tap_map[tap]], full_bar + stage, cc * TC_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
           }
           tma_load_2d(sb, &p.tma_b, full_bar + stage, kb * TC_BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        MMG_TR(8, w_empty); MMG_TR(9, MMG_CLK());
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = idesc_bf16_f32(TC_BM, BN, false, false);
+  } else if (warp == 1 && pair_rank == 0) {
+    // ===================== MMA issuer (PAIR: the leader CTA issues for both SMs) =====================
+    constexpr uint32_t idesc = idesc_bf16_f32(PAIR ? 2 * TC_BM : TC_BM, BN, false, false);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+    [[maybe_unused]] int tile_i = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_i) {
+      if (lane == 0) MMG_TR(0, MMG_CLK());
+      if (PAIR) mbar_wait_cluster(tmem_empty + acc, acc_phase ^ 1);    // released by the epilogue warps of BOTH CTAs
+      else mbar_wait(tmem_empty + acc, acc_phase ^ 1);
       tc_fence_after();
+      if (lane == 0) MMG_TR(1, MMG_CLK());
+      [[maybe_unused]] long long w_full = 0;
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(full_bar + stage, phase);
+        { [[maybe_unused]] const long long t0 = MMG_CLK(); mbar_wait(full_bar + stage, phase); w_full += MMG_CLK() - t0; }
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = smem_desc_kmajor_sw128(sa);
           const uint64_t bdesc = smem_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+          if (PAIR) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)
+              umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            umma_commit_pair(empty_bar + stage, 3);                       // the slot is free in both CTAs once these MMAs retire
+            if (kb == p.num_kb - 1) umma_commit_pair(tmem_full + acc, 3); // each CTA's epilogue reads its own half of the accumulator
+          } else {
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
             umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           umma_commit(empty_bar + stage);                         // smem slot free once these MMAs retire
           if (kb == p.num_kb - 1) umma_commit(tmem_full + acc);   // accumulator ready for the epilogue
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (lane == 0) { MMG_TR(2, w_full); MMG_TR(3, MMG_CLK()); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -157,13 +214,24 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     const int half = (warp - 4) >> 2;             // 0: even 64-column chunks, 1: odd chunks
     const int r_in_tile = quarter * 32 + lane;
     Epilogue epi = p.epi;
+    // Coalescing through the per-warp staging tile pays where the epilogue is nothing but a wide store: fp32 outputs (the logits
+    // GEMM: tile period 11 250 -> 9 250 cycles).  Measured slower for the bf16 / residual epilogues, whose tiles then spend the
+    // saved L1 wavefronts on the extra shared-memory round trips: those keep the direct row-per-thread path.
+    static const bool stage_all = false;
+    const bool use_ws = !LNF && (stage_all || (epi.kind == MMG_EPI_STORE && epi.p.out_dtype == MMG_F32));
+    epi.ws = use_ws ? reinterpret_cast<uint4*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 4) * 256 : nullptr;
     if (epi.kind == MMG_EPI_QKV) { epi.p.q_scale = s_scale; epi.p.k_scale = s_scale + 64; }
     const bool whole_row = (epi.kind == MMG_EPI_CONVT_RGB);      // needs every chunk of a row in one thread
     const bool prefetch_resid = epi.can_prefetch_resid();
+    const bool stg = prefetch_resid && epi.resid_staged();       // residual rows read and written through the staging tile (coalesced)
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t stats_phase = 0; int stats_buf = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m_blk = LNF ? tile : tile % p.num_m_tiles, n_blk = LNF ? my_rank : tile / p.num_m_tiles;
+    [[maybe_unused]] int tile_i = 0;
+    [[maybe_unused]] const bool tr = (warp == 4 && lane == 0);
+    const uint32_t tmem_empty0 = PAIR ? mapa_shared(smem_u32(tmem_empty), 0) : 0u;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_i) {
+      const int m_blk = LNF ? tile : PAIR ? 2 * (tile % num_pm) + pair_rank : tile % p.num_m_tiles;
+      const int n_blk = LNF ? my_rank : tile / num_pm;
       int64_t row; bool valid;
       if (p.mode == 0) {
         row = (int64_t)m_blk * TC_BM + r_in_tile; valid = row < p.M;
@@ -176,12 +244,18 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       }
       const bool mine = !whole_row || half == 0;
       const int c_first = whole_row ? 0 : half, c_step = whole_row ? 1 : 2;
-      const bool pre = prefetch_resid && valid && mine && (n_blk * BN + c_first * 64 < p.N) && c_first < BN / 64;
-      float rbuf[64];
+      const bool pre_u = prefetch_resid && mine && (n_blk * BN + c_first * 64 < p.N) && c_first < BN / 64;     // warp-uniform
+      const bool pre = pre_u && valid;
+      uint4 rb[16];                                                        // the residual chunk: transposed 16-byte pieces (staged) ...
+      float (&rbuf)[64] = *reinterpret_cast<float (*)[64]>(&rb[0]);       // ... or this row's 64 values (direct)
       float ln_sum = 0.f, ln_sq = 0.f;
-      if (pre) epi.load_resid(row, n_blk * BN + c_first * 64, rbuf);      // in flight while the MMA of this tile completes
+      // in flight while the MMA of this tile completes
+      if (stg) { if (pre_u) epi.load_resid_w(row, n_blk * BN + c_first * 64, valid, rb); }
+      else if (pre) epi.load_resid(row, n_blk * BN + c_first * 64, rbuf);
+      if (tr) MMG_TR(4, MMG_CLK());
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
+      if (tr) MMG_TR(5, MMG_CLK());
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       if (valid && mine) epi.begin_row(row);
       bool released = false;
@@ -195,11 +269,19 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         if (c + c_step >= BN / 64) {               // last chunk is in registers: hand the accumulator stage back before the math
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty + acc);
+          if (lane == 0) { if (PAIR) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u); else mbar_arrive(tmem_empty + acc); }
+          if (tr) MMG_TR(6, MMG_CLK());
           released = true;
         }
         const int col0 = n_blk * BN + c * 64;
-        if (valid && col0 < p.N) {
+        if (col0 < p.N && stg) {
+          epi.fuse_resid_w(col0, v, rb);
+          const int cn = col0 + c_step * 64;
+          if (c + c_step < BN / 64 && cn < p.N) epi.load_resid_w(row, cn, valid, rb);          // next chunk's residual overlaps the stores
+          epi.store_f32_w(row, col0, v, valid);
+        } else if (col0 < p.N && !prefetch_resid) {
+          epi.template apply<true>(row, col0, v, 64, valid);
+        } else if (valid && col0 < p.N) {
           if (prefetch_resid) {
             epi.fuse_resid(col0, v, rbuf);
             const int cn = col0 + c_step * 64;
@@ -219,10 +301,11 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         }
       }
       if (valid && mine) epi.end_row(row);
+      if (tr) MMG_TR(7, MMG_CLK());
       if (!released) {                             // warps that own no chunk of this tile
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty + acc);
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u); else mbar_arrive(tmem_empty + acc); }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (LNF) {
@@ -264,8 +347,8 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (LNF) cluster_sync_all();                  // no CTA may exit while its peer can still write its shared memory
-  if (warp == 1) { tc_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
+  if (LNF || PAIR) cluster_sync_all();          // no CTA may exit while its peer can still write its shared memory / read its operands
+  if (warp == 1) { tc_fence_after(); if (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base); else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
 }
 
 }  // namespace mmg

@@ -103,21 +103,51 @@ vq_l2_argmin_kernel(const float* __restrict__ x, const float* __restrict__ cb, u
 }
 
 // ids -> +-1 codes -> project_out (LFQ.indices_to_codes): out[t, c] = b_out[c] + sum_i (+-1)_i w_out[c, i]
+// A thread keeps the `bits` weights of two adjacent output channels in registers and walks a slice of DEC_TOK tokens (ids staged in
+// shared memory, sign masks uniform across the block): the projection is read once per CTA instead of once per token.
+constexpr int DEC_TOK = 64, DEC_MAXB = 24;
 template <typename T>
 __global__ void __launch_bounds__(256)
 vq_decode_codes_kernel(const int64_t* __restrict__ ids, const float* __restrict__ w_out, const float* __restrict__ b_out, T* __restrict__ out,
                        int64_t tokens, int D, int bits) {
-  const int64_t t = blockIdx.x;
-  const int64_t id = ids[t];
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float acc;
-    if (w_out) {
-      acc = b_out ? b_out[c] : 0.f;
-      for (int i = 0; i < bits; ++i) { const float w = __ldg(w_out + (int64_t)c * bits + i); acc += ((id >> (bits - 1 - i)) & 1) ? w : -w; }
-    } else {
-      acc = ((id >> (bits - 1 - c)) & 1) ? 1.f : -1.f;
+  __shared__ int64_t sid[DEC_TOK];
+  const int64_t t0 = (int64_t)blockIdx.y * DEC_TOK;
+  const int nt = (int)((tokens - t0) < DEC_TOK ? (tokens - t0) : DEC_TOK);
+  if (threadIdx.x < nt) sid[threadIdx.x] = ids[t0 + threadIdx.x];
+  __syncthreads();
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
+  if (c >= D) return;
+  const bool two = c + 1 < D;
+  if (!w_out) {                                  // identity projection (D == bits): the code itself
+    for (int t = 0; t < nt; ++t) {
+      const int64_t id = sid[t];
+      out[(t0 + t) * D + c] = from_f<T>(((id >> (bits - 1 - c)) & 1) ? 1.f : -1.f);
+      if (two) out[(t0 + t) * D + c + 1] = from_f<T>(((id >> (bits - 2 - c)) & 1) ? 1.f : -1.f);
     }
-    out[t * D + c] = from_f<T>(acc);
+    return;
+  }
+  uint32_t w0[DEC_MAXB], w1[DEC_MAXB];
+#pragma unroll
+  for (int i = 0; i < DEC_MAXB; ++i) {
+    w0[i] = i < bits ? __float_as_uint(__ldg(w_out + (int64_t)c * bits + i)) : 0u;
+    w1[i] = (i < bits && two) ? __float_as_uint(__ldg(w_out + (int64_t)(c + 1) * bits + i)) : 0u;
+  }
+  const float b0 = b_out ? b_out[c] : 0.f, b1 = (b_out && two) ? b_out[c + 1] : 0.f;
+  for (int t = 0; t < nt; ++t) {
+    const uint32_t nid = ~(uint32_t)sid[t];       // bit set -> the code component is -1 -> flip the weight's sign
+    float a0 = b0, a1 = b1;
+#pragma unroll
+    for (int i = 0; i < DEC_MAXB; ++i) {
+      if (i < bits) {
+        const uint32_t sg = ((nid >> (bits - 1 - i)) & 1u) << 31;
+        a0 += __uint_as_float(w0[i] ^ sg); a1 += __uint_as_float(w1[i] ^ sg);
+      }
+    }
+    T* o = out + (t0 + t) * D + c;
+    if (two && (reinterpret_cast<uintptr_t>(o) % (2 * sizeof(T))) == 0) {
+      if constexpr (sizeof(T) == 2) { __nv_bfloat162 v = __floats2bfloat162_rn(a0, a1); *reinterpret_cast<__nv_bfloat162*>(o) = v; }
+      else *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
+    } else { o[0] = from_f<T>(a0); if (two) o[1] = from_f<T>(a1); }
   }
 }
 
@@ -166,10 +196,11 @@ extern "C" int mmg_vq_l2_argmin(const mmg_vq_l2_argmin_args* a, void* stream) {
 extern "C" int mmg_vq_decode_codes(const mmg_vq_decode_codes_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MMG_CHECK_ARG(a && a->ids && a->out, "mmg_vq_decode_codes: NULL pointer");
-  MMG_CHECK_ARG(a->bits >= 1 && a->bits <= 62 && (a->w_out || a->D == a->bits), "mmg_vq_decode_codes: bits / identity projection");
+  MMG_CHECK_ARG(a->bits >= 1 && a->bits <= DEC_MAXB && (a->w_out || a->D == a->bits), "mmg_vq_decode_codes: bits (<= 24) / identity projection");
   if (a->T == 0) return MMG_OK;
-  if (a->dtype == MMG_BF16) vq_decode_codes_kernel<bf16><<<(unsigned)a->T, 256, 0, st>>>(a->ids, a->w_out, a->b_out, (bf16*)a->out, a->T, a->D, a->bits);
-  else vq_decode_codes_kernel<float><<<(unsigned)a->T, 256, 0, st>>>(a->ids, a->w_out, a->b_out, (float*)a->out, a->T, a->D, a->bits);
+  const dim3 grid((unsigned)((a->D + 511) / 512), (unsigned)((a->T + DEC_TOK - 1) / DEC_TOK));
+  if (a->dtype == MMG_BF16) vq_decode_codes_kernel<bf16><<<grid, 256, 0, st>>>(a->ids, a->w_out, a->b_out, (bf16*)a->out, a->T, a->D, a->bits);
+  else vq_decode_codes_kernel<float><<<grid, 256, 0, st>>>(a->ids, a->w_out, a->b_out, (float*)a->out, a->T, a->D, a->bits);
   MMG_LAUNCHED();
   return MMG_OK;
 }
