@@ -68,9 +68,9 @@ struct Epilogue {
     for (int j = 0; j < 8; ++j) d[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
   }
   // 64 accumulator columns of this lane's row -> dst (T = float: 256 B, T = bf16: 128 B); collective when staged
-  template <typename T>
+  template <bool WS, typename T>
   __device__ __forceinline__ void store64(T* dst, const float (&v)[64], bool valid) const {
-    if (ws != nullptr) {
+    if (WS) {
       uint4 d[8];
       if constexpr (sizeof(T) == 4) {
         pack32_f32(v, d);      wstore<8>(valid ? (void*)dst : nullptr, d);
@@ -82,14 +82,15 @@ struct Epilogue {
       Vec64<T>::store(dst, v);
     }
   }
+  template <bool WS>
   __device__ __forceinline__ bool staged(const void* base, int64_t ld_elems, int esize) const {    // warp-uniform
-    return ws != nullptr && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && ((ld_elems * esize) & 15) == 0;
+    return WS && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && ((ld_elems * esize) & 15) == 0;
   }
 
-  template <typename T>
+  template <bool WS, typename T>
   __device__ __forceinline__ void store_n(T* dst, const float (&v)[64], int n, bool vec_ok, bool valid, bool stage_ok) const {
     if (vec_ok && n == 64) {
-      if (stage_ok) store64(dst, v, valid);
+      if (WS && stage_ok) store64<WS>(dst, v, valid);
       else if (valid) Vec64<T>::store(dst, v);
     } else if (valid) {
 #pragma unroll
@@ -125,10 +126,11 @@ struct Epilogue {
 
   // row: global output row (< M). col0: first accumulator column of this chunk (multiple of 64). nvalid: columns < N.
   // valid == false: this lane's row is outside the matrix; it still takes part in the warp-collective staged stores.
-  template <bool FAST>
+  // WS: the kernel gave this warp a staging tile (`ws`) -> coalesced stores; compiled out otherwise.
+  template <bool FAST, bool WS = false>
   __device__ __forceinline__ void apply(int64_t row, int col0, float (&v)[64], int nvalid, bool valid = true) {
     const bool bf = (p.out_dtype == MMG_BF16);
-    const bool coll = ws != nullptr && (kind == MMG_EPI_STORE || kind == MMG_EPI_RESIDUAL || kind == MMG_EPI_GEGLU || kind == MMG_EPI_GLU ||
+    const bool coll = WS && (kind == MMG_EPI_STORE || kind == MMG_EPI_RESIDUAL || kind == MMG_EPI_GEGLU || kind == MMG_EPI_GLU ||
                                         kind == MMG_EPI_QKV || kind == MMG_EPI_CONVT);
     if (!valid && !coll) return;
     switch (kind) {
@@ -206,8 +208,8 @@ struct Epilogue {
 #pragma unroll
           for (int i = 0; i < 64; ++i) v[i] = leaky01(v[i]);
         }
-        if (bf) store_n(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col0, v, nvalid, vec_ok, valid, staged(p.out, p.ldo, 2));
-        else    store_n(reinterpret_cast<float*>(p.out) + row * p.ldo + col0, v, nvalid, vec_ok, valid, staged(p.out, p.ldo, 4));
+        if (bf) store_n<WS>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col0, v, nvalid, vec_ok, valid, staged<WS>(p.out, p.ldo, 2));
+        else    store_n<WS>(reinterpret_cast<float*>(p.out) + row * p.ldo + col0, v, nvalid, vec_ok, valid, staged<WS>(p.out, p.ldo, 4));
         break;
       }
       case MMG_EPI_GEGLU:
@@ -229,7 +231,7 @@ struct Epilogue {
           }
         }
         const int oc = col0 >> 1;
-        if (bf && staged(p.out, p.ldo, 2)) {            // 32 bf16 = 64 B per row and chunk
+        if (bf && staged<WS>(p.out, p.ldo, 2)) {        // 32 bf16 = 64 B per row and chunk
           uint4 q4[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) q4[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]), pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
@@ -271,8 +273,8 @@ struct Epilogue {
 #pragma unroll
           for (int i = 0; i < 64; ++i) v[i] = v[i] * inv * sc[i];
         }
-        if (bf) { if (staged(dst, 64, 2)) store64(reinterpret_cast<bf16*>(dst) + off, v, valid); else if (valid) Vec64<bf16>::store(reinterpret_cast<bf16*>(dst) + off, v); }
-        else    { if (staged(dst, 64, 4)) store64(reinterpret_cast<float*>(dst) + off, v, valid); else if (valid) Vec64<float>::store(reinterpret_cast<float*>(dst) + off, v); }
+        if (bf) { if (staged<WS>(dst, 64, 2)) store64<WS>(reinterpret_cast<bf16*>(dst) + off, v, valid); else if (valid) Vec64<bf16>::store(reinterpret_cast<bf16*>(dst) + off, v); }
+        else    { if (staged<WS>(dst, 64, 4)) store64<WS>(reinterpret_cast<float*>(dst) + off, v, valid); else if (valid) Vec64<float>::store(reinterpret_cast<float*>(dst) + off, v); }
         if (valid && t == 0 && hc >= p.nq_heads) {              // learned null key / value -> key row 0 (muse_maskgit_pytorch.py:145-149)
           const void* nsrc = (hc < p.nq_heads + p.nk_heads) ? p.null_k : p.null_v;
           if (nsrc) {
@@ -300,8 +302,8 @@ struct Epilogue {
           const int64_t b = r_b; const int rem = r_t; const int y = rem / p.W, x = rem - y * p.W;
           const int64_t opix = (b * 2 * p.H + 2 * y + p.py) * (int64_t)(2 * p.W) + 2 * x + p.px;
           const bool vec_ok = (nvalid == 64) && ((p.ldo & 7) == 0);
-          if (bf) store_n(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + col0, v, nvalid, vec_ok, valid, staged(p.out, p.ldo, 2));
-          else    store_n(reinterpret_cast<float*>(p.out) + opix * p.ldo + col0, v, nvalid, vec_ok, valid, staged(p.out, p.ldo, 4));
+          if (bf) store_n<WS>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + col0, v, nvalid, vec_ok, valid, staged<WS>(p.out, p.ldo, 2));
+          else    store_n<WS>(reinterpret_cast<float*>(p.out) + opix * p.ldo + col0, v, nvalid, vec_ok, valid, staged<WS>(p.out, p.ldo, 4));
         } else {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -338,7 +340,8 @@ struct Epilogue {
     }
   }
   // staged (coalesced) variants of the three calls above; collective, valid == false lanes contribute nothing
-  __device__ __forceinline__ bool resid_staged() const { return staged(p.resid, p.ldr, 4) && staged(p.out, p.ldo, 4); }
+  template <bool WS>
+  __device__ __forceinline__ bool resid_staged() const { return staged<WS>(p.resid, p.ldr, 4) && staged<WS>(p.out, p.ldo, 4); }
   __device__ __forceinline__ void load_resid_w(int64_t row, int col0, bool valid, uint4 (&rb)[16]) const {
     const float* src = reinterpret_cast<const float*>(p.resid) + row * p.ldr + col0;
     uint4 (&lo)[8] = *reinterpret_cast<uint4 (*)[8]>(&rb[0]);
@@ -364,7 +367,7 @@ struct Epilogue {
     }
   }
   __device__ __forceinline__ void store_f32_w(int64_t row, int col0, const float (&v)[64], bool valid) const {
-    store64(reinterpret_cast<float*>(p.out) + row * p.ldo + col0, v, valid);
+    store64<true>(reinterpret_cast<float*>(p.out) + row * p.ldo + col0, v, valid);
   }
   __device__ __forceinline__ void load_out_f32(int64_t row, int col0, float (&v)[64]) const {
     Vec64<float>::load(reinterpret_cast<const float*>(p.out) + row * p.ldo + col0, v);

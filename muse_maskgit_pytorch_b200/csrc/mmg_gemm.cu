@@ -18,16 +18,31 @@ static int launch_tc(const TcGemmParams& p, cudaStream_t st) {
   return MMG_OK;
 }
 
+// staged-store variant (coalesced epilogue stores through shared memory): pays where the epilogue is nothing but a wide store,
+// i.e. fp32 outputs (the logits GEMM: tile period 11 250 -> 9 250 cycles); measured slower for the bf16 / residual epilogues
+template <int BN>
+static int launch_tc_staged(const TcGemmParams& p, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES_STAGED); });
+  if (attr_err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(tc_gemm_staged<%d>): %s", BN, cudaGetErrorString(attr_err));
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  MMG_CUDA(launch_pdl(tc_gemm_kernel<BN, false, false, true>, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES_STAGED, st, p));
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
 // LayerNorm-fused variant: clusters of two CTAs (column halves of the same rows), grid = 2 * min(#m-tiles, #SM / 2)
 template <int BN>
 static int launch_tc_lnf(const TcGemmParams& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES_LNF); });
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES); });
   if (attr_err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(tc_gemm_lnf<%d>): %s", BN, cudaGetErrorString(attr_err));
   const int pairs = p.num_m_tiles < num_sms() / 2 ? p.num_m_tiles : num_sms() / 2;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<BN>::SMEM_BYTES_LNF; cfg.stream = st;
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<BN>::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
@@ -93,6 +108,9 @@ static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; uint64_t str[1] = {(uint64_t)ldw * 2}; uint32_t box[2] = {TC_BK, (uint32_t)(pair ? bn / 2 : bn)};
   int rc = make_tmap_bf16(&p.tma_b, w, 2, dims, str, box); if (rc) return rc;
   if (pair) return launch_tc_pair<256>(p, st);
+  static const int staged_forced = [] { const char* e = getenv("MMG_GEMM_STAGED"); return e ? atoi(e) : -1; }();
+  const bool plain_f32 = p.epi.kind == MMG_EPI_STORE && p.epi.p.out_dtype == MMG_F32;
+  if (bn == 256 && staged_forced != 0 && (plain_f32 || (staged_forced == 1 && p.epi.kind != MMG_EPI_CONVT_RGB))) return launch_tc_staged<256>(p, st);
   switch (bn) {
     case 64: return launch_tc<64>(p, st);
     case 128: return launch_tc<128>(p, st);

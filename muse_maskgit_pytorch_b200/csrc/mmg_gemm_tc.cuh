@@ -54,26 +54,28 @@ template <int BN> struct TcCfg {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = TC_EPI_WARPS * 4096;    // one 32-row x 128-byte transpose tile per epilogue warp (mmg_epilogue.cuh)
-  static constexpr int SMEM_BYTES_LNF = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int SMEM_BYTES = SMEM_BYTES_LNF + STAGING_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES_STAGED = SMEM_BYTES + STAGING_BYTES;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   // CTA pair (cta_group::2, M = 256 over two SMs): each CTA stages its own 128 rows of A and HALF of the W tile, so a k-block costs
   // 32 KB of L2->SM traffic per SM instead of 48 KB and six stages fit where four did
   static constexpr int PAIR_STAGES = 6;
   static constexpr int PAIR_STAGE_BYTES = A_BYTES + B_BYTES / 2;
-  static constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256 + STAGING_BYTES;
+  static constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256;
 };
 
 // LNF: the epilogue additionally emits LayerNorm(out row) as bf16 (see mmg_epilogue_args::ln_out).  Launched as clusters of two
 // CTAs that own the two column halves (N == 2 * BN) of the same 128 rows; per-row (sum, sumsq) partials cross through DSMEM.
 // PAIR: launched as clusters of two CTAs that form one tcgen05 CTA pair: a 256 x BN output tile per pair, the leader (rank 0) issues
 // the MMAs for both SMs, TMA completions of both CTAs are counted on the leader's barriers, MMA commits are multicast to both.
-template <int BN, bool LNF = false, bool PAIR = false>
+// STAGED: the epilogue warps own a shared-memory staging tile each and write their rows through it (coalesced; mmg_epilogue.cuh).
+template <int BN, bool LNF = false, bool PAIR = false, bool STAGED = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   using namespace sm100;
   using Cfg = TcCfg<BN>;
   static_assert(!(LNF && PAIR), "LayerNorm fusion and CTA pairs both claim the cluster");
+  static_assert(!(LNF && STAGED), "the LayerNorm-fused kernel has no room for the staging tiles");
   constexpr int STAGES = PAIR ? Cfg::PAIR_STAGES : Cfg::STAGES;
   constexpr int STAGE_BYTES = PAIR ? Cfg::PAIR_STAGE_BYTES : Cfg::STAGE_BYTES;
 
@@ -214,16 +216,11 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     const int half = (warp - 4) >> 2;             // 0: even 64-column chunks, 1: odd chunks
     const int r_in_tile = quarter * 32 + lane;
     Epilogue epi = p.epi;
-    // Coalescing through the per-warp staging tile pays where the epilogue is nothing but a wide store: fp32 outputs (the logits
-    // GEMM: tile period 11 250 -> 9 250 cycles).  Measured slower for the bf16 / residual epilogues, whose tiles then spend the
-    // saved L1 wavefronts on the extra shared-memory round trips: those keep the direct row-per-thread path.
-    static const bool stage_all = false;
-    const bool use_ws = !LNF && (stage_all || (epi.kind == MMG_EPI_STORE && epi.p.out_dtype == MMG_F32));
-    epi.ws = use_ws ? reinterpret_cast<uint4*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 4) * 256 : nullptr;
+    epi.ws = STAGED ? reinterpret_cast<uint4*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 4) * 256 : nullptr;
     if (epi.kind == MMG_EPI_QKV) { epi.p.q_scale = s_scale; epi.p.k_scale = s_scale + 64; }
     const bool whole_row = (epi.kind == MMG_EPI_CONVT_RGB);      // needs every chunk of a row in one thread
     const bool prefetch_resid = epi.can_prefetch_resid();
-    const bool stg = prefetch_resid && epi.resid_staged();       // residual rows read and written through the staging tile (coalesced)
+    const bool stg = STAGED && prefetch_resid && epi.template resid_staged<STAGED>();       // residual rows read and written through the staging tile (coalesced)
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t stats_phase = 0; int stats_buf = 0;
     [[maybe_unused]] int tile_i = 0;
@@ -274,13 +271,13 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
           released = true;
         }
         const int col0 = n_blk * BN + c * 64;
-        if (col0 < p.N && stg) {
+        if (STAGED && col0 < p.N && stg) {
           epi.fuse_resid_w(col0, v, rb);
           const int cn = col0 + c_step * 64;
           if (c + c_step < BN / 64 && cn < p.N) epi.load_resid_w(row, cn, valid, rb);          // next chunk's residual overlaps the stores
           epi.store_f32_w(row, col0, v, valid);
-        } else if (col0 < p.N && !prefetch_resid) {
-          epi.template apply<true>(row, col0, v, 64, valid);
+        } else if (STAGED && col0 < p.N && !prefetch_resid) {
+          epi.template apply<true, STAGED>(row, col0, v, 64, valid);
         } else if (valid && col0 < p.N) {
           if (prefetch_resid) {
             epi.fuse_resid(col0, v, rbuf);

@@ -175,25 +175,27 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   if ((V & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
     const float4* r4 = reinterpret_cast<const float4*>(row);
     const int n4 = V >> 2;
-    constexpr int UNR = 4;                                          // 4 independent 128-bit loads per thread, next group prefetched
-    float4 nxt[UNR];
+    constexpr int UNR = 4;                                          // 4 independent 128-bit loads per thread and group
+    constexpr int GRP = SMP_THREADS * UNR;                          // float4s per group (16 elements per thread)
+    // one group of 16 elements per thread: load (the whole group in range: no padding moves) ...
+    auto load_group = [&](float4 (&g)[UNR], int i0) {
+      if (i0 + GRP <= n4) {
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int i = u * SMP_THREADS + tid;
-      nxt[u] = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
-      if (i < n4) nxt[u] = ld_stream4(r4 + i);
-    }
-    for (int i0 = 0; i0 < n4; i0 += SMP_THREADS * UNR) {
-      float xs[UNR * 4];
+        for (int u = 0; u < UNR; ++u) g[u] = ld_stream4(r4 + i0 + u * SMP_THREADS + tid);
+      } else {
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) { xs[4 * u] = nxt[u].x; xs[4 * u + 1] = nxt[u].y; xs[4 * u + 2] = nxt[u].z; xs[4 * u + 3] = nxt[u].w; }
-      const bool full = i0 + SMP_THREADS * UNR <= n4;                 // block-uniform: every thread's 16 elements are in range
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {                                // prefetch the following group while this one is processed
-        const int i = i0 + SMP_THREADS * UNR + u * SMP_THREADS + tid;
-        nxt[u] = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
-        if (i < n4) nxt[u] = ld_stream4(r4 + i);
+        for (int u = 0; u < UNR; ++u) {
+          const int i = i0 + u * SMP_THREADS + tid;
+          g[u] = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
+          if (i < n4) g[u] = ld_stream4(r4 + i);
+        }
       }
+    };
+    // ... and consume: online softmax statistics + append the elements >= tlo to the candidate list
+    auto consume_group = [&](const float4 (&g)[UNR], int i0) {
+      const float xs[UNR * 4] = {g[0].x, g[0].y, g[0].z, g[0].w, g[1].x, g[1].y, g[1].z, g[1].w,
+                                 g[2].x, g[2].y, g[2].z, g[2].w, g[3].x, g[3].y, g[3].z, g[3].w};
+      const bool full = i0 + GRP <= n4;                              // block-uniform: every thread's 16 elements are in range
       const bool has = full || (i0 + tid) < n4;                      // a thread with no element must not touch the statistics:
       float lm = xs[0];                                              // fma(-1e30, log2e, -fl(-1e30 * log2e)) is a huge rounding residue
 #pragma unroll
@@ -220,7 +222,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
       const int c = __popc(mask);
       if (mask) {
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) scr[u * SMP_THREADS + tid] = make_float4(xs[4 * u], xs[4 * u + 1], xs[4 * u + 2], xs[4 * u + 3]);
+        for (int u = 0; u < UNR; ++u) scr[u * SMP_THREADS + tid] = g[u];
       }
       int incl = c;
 #pragma unroll
@@ -239,6 +241,16 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
           ++start;
         }
       }
+    };
+    // two register groups in ping-pong: the loads of one are in flight while the other is consumed (no register copies)
+    float4 ga[UNR], gb[UNR];
+    load_group(ga, 0);
+    for (int i0 = 0; i0 < n4; i0 += 2 * GRP) {
+      const bool second = i0 + GRP < n4;                            // block-uniform
+      if (second) load_group(gb, i0 + GRP);
+      consume_group(ga, i0);
+      if (i0 + 2 * GRP < n4) load_group(ga, i0 + 2 * GRP);
+      if (second) consume_group(gb, i0 + GRP);
     }
   } else {
     for (int i0 = 0; i0 < V; i0 += SMP_THREADS) {
