@@ -339,6 +339,21 @@ struct Epilogue {
       for (int i = 0; i < 64; ++i) v[i] += r[i] + (p.bias ? __ldg(p.bias + col0 + i) : 0.f);
     }
   }
+  // residual epilogues as an in-place reduction (out == resid): v <- the term added to the row; the caller pushes it with
+  // cp.reduce.async.bulk (fp32 add in L2), so the residual row is never read and nothing goes through the L1 wavefront path
+  __device__ __forceinline__ bool can_reduce_in_place() const {
+    return can_prefetch_resid() && p.out == p.resid && p.ldo == p.ldr && p.out_dtype == MMG_F32 && (p.ldo & 3) == 0 &&
+           (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+  }
+  __device__ __forceinline__ void resid_term(int col0, float (&v)[64]) const {
+    if (kind == MMG_EPI_LNFOLD_RESIDUAL) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = st_b * (v[i] - st_a * __ldg(p.bias + col0 + i));
+    } else if (p.bias) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] += __ldg(p.bias + col0 + i);
+    }
+  }
   // staged (coalesced) variants of the three calls above; collective, valid == false lanes contribute nothing
   template <bool WS>
   __device__ __forceinline__ bool resid_staged() const { return staged<WS>(p.resid, p.ldr, 4) && staged<WS>(p.out, p.ldo, 4); }

@@ -5,6 +5,8 @@
 
 namespace mmg {
 
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 template <int BN>
 static int launch_tc(const TcGemmParams& p, cudaStream_t st) {
   static std::once_flag once;
@@ -24,11 +26,25 @@ template <int BN>
 static int launch_tc_staged(const TcGemmParams& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES_STAGED); });
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES_STAGED); });
   if (attr_err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(tc_gemm_staged<%d>): %s", BN, cudaGetErrorString(attr_err));
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  MMG_CUDA(launch_pdl(tc_gemm_kernel<BN, false, false, true>, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES_STAGED, st, p));
+  MMG_CUDA(launch_pdl(tc_gemm_kernel<BN, false, false, 1>, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES_STAGED, st, p));
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
+// in-place reduction epilogue (x += A W^T through cp.reduce.async.bulk): the residual GEMMs of the transformer blocks
+template <int BN>
+static int launch_tc_red(const TcGemmParams& p, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES_RED); });
+  if (attr_err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(tc_gemm_red<%d>): %s", BN, cudaGetErrorString(attr_err));
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  MMG_CUDA(launch_pdl(tc_gemm_kernel<BN, false, false, 2>, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES_RED, st, p));
   MMG_LAUNCHED();
   return MMG_OK;
 }
@@ -104,6 +120,10 @@ static int pick_bn(int64_t M_tiles, int64_t N, int epilogue) {
 
 static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_t K, int64_t ldw, cudaStream_t st) {
   p.num_n_tiles = (int)((N + bn - 1) / bn);
+  {
+    static const int nfast_forced = [] { const char* e = getenv("MMG_GEMM_NFAST"); return e ? atoi(e) : -1; }();
+    p.n_fast = nfast_forced >= 0 ? nfast_forced : ((int64_t)N * K * 2 <= (8 << 20) && p.num_n_tiles > 1 && p.num_n_tiles <= 16) ? 1 : 0;
+  }
   const bool pair = use_pair(p, bn);
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; uint64_t str[1] = {(uint64_t)ldw * 2}; uint32_t box[2] = {TC_BK, (uint32_t)(pair ? bn / 2 : bn)};
   int rc = make_tmap_bf16(&p.tma_b, w, 2, dims, str, box); if (rc) return rc;
@@ -111,6 +131,13 @@ static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_
   static const int staged_forced = [] { const char* e = getenv("MMG_GEMM_STAGED"); return e ? atoi(e) : -1; }();
   const bool plain_f32 = p.epi.kind == MMG_EPI_STORE && p.epi.p.out_dtype == MMG_F32;
   if (bn == 256 && staged_forced != 0 && (plain_f32 || (staged_forced == 1 && p.epi.kind != MMG_EPI_CONVT_RGB))) return launch_tc_staged<256>(p, st);
+  static const int red_forced = [] { const char* e = getenv("MMG_GEMM_RED"); return e ? atoi(e) : -1; }();
+  const mmg_epilogue_args& e = p.epi.p;
+  const bool in_place = (p.epi.kind == MMG_EPI_LNFOLD_RESIDUAL || (p.epi.kind == MMG_EPI_RESIDUAL && e.act == 0)) && e.out_dtype == MMG_F32 &&
+                        e.out == e.resid && e.ldo == e.ldr && (e.ldo % 4) == 0 && aligned16(e.out) && !e.ln_out;
+  if (in_place && red_forced != 0) {
+    switch (bn) { case 64: return launch_tc_red<64>(p, st); case 128: return launch_tc_red<128>(p, st); case 256: return launch_tc_red<256>(p, st); }
+  }
   switch (bn) {
     case 64: return launch_tc<64>(p, st);
     case 128: return launch_tc<128>(p, st);
@@ -207,7 +234,6 @@ static int launch_simt(int dtype, const void* a, const void* w, int64_t M, int64
   return MMG_OK;
 }
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // conv tap tables.  kind 0: 1x1; 1: 3x3 s1 p1; 2: 4x4 s2 p1; 3: 5x5 s1 p2.  Tap index t = r*kw + s (weights packed tap-major).
 static void conv_geom(int kind, int B, int H, int W, int Cin, ConvGeom* g) {

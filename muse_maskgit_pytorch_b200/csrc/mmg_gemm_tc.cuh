@@ -30,6 +30,9 @@ struct alignas(64) TcGemmParams {
   int64_t M, N;
   int num_kb, num_m_tiles, num_n_tiles;
   int mode;                 // 0 dense, 1 conv (4-D A maps)
+  int n_fast;               // tile order: 0 = consecutive tiles walk M (the W tile is shared by the CTAs in flight: huge N, e.g. the logits
+                            // GEMM), 1 = consecutive tiles walk N (all column tiles of an A row block run together, so A streams from HBM once:
+                            // small W that stays L2 resident, e.g. the N = 512 residual GEMMs)
   int cchunks, ntaps;       // conv: k-block = tap * cchunks + channel chunk
   int8_t tap_map[TC_MAX_TAPS], tap_dy[TC_MAX_TAPS], tap_dx[TC_MAX_TAPS];
   int TW, TH, TB, tiles_x, tiles_y;   // conv: tile = TB images x TH rows x TW cols of the OUTPUT grid (Ho x Wo)
@@ -56,6 +59,11 @@ template <int BN> struct TcCfg {
   static constexpr int STAGING_BYTES = TC_EPI_WARPS * 4096;    // one 32-row x 128-byte transpose tile per epilogue warp (mmg_epilogue.cuh)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int SMEM_BYTES_STAGED = SMEM_BYTES + STAGING_BYTES;
+  // in-place reduction epilogue (EPI_MODE 2): one 144-byte row buffer per epilogue thread; these GEMMs are bound by their epilogue,
+  // not by the operand ring, so they give up ring stages for it
+  static constexpr int RED_STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
+  static constexpr int RED_ROW_BYTES = 144;
+  static constexpr int SMEM_BYTES_RED = RED_STAGES * STAGE_BYTES + 1024 + 256 + TC_EPI_WARPS * 32 * RED_ROW_BYTES;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   // CTA pair (cta_group::2, M = 256 over two SMs): each CTA stages its own 128 rows of A and HALF of the W tile, so a k-block costs
   // 32 KB of L2->SM traffic per SM instead of 48 KB and six stages fit where four did
@@ -68,15 +76,18 @@ template <int BN> struct TcCfg {
 // CTAs that own the two column halves (N == 2 * BN) of the same 128 rows; per-row (sum, sumsq) partials cross through DSMEM.
 // PAIR: launched as clusters of two CTAs that form one tcgen05 CTA pair: a 256 x BN output tile per pair, the leader (rank 0) issues
 // the MMAs for both SMs, TMA completions of both CTAs are counted on the leader's barriers, MMA commits are multicast to both.
-// STAGED: the epilogue warps own a shared-memory staging tile each and write their rows through it (coalesced; mmg_epilogue.cuh).
-template <int BN, bool LNF = false, bool PAIR = false, bool STAGED = false>
+// EPI_MODE 1 (STAGED): the epilogue warps own a shared-memory staging tile each and write their rows through it (coalesced;
+// mmg_epilogue.cuh).  EPI_MODE 2 (RED): in-place residual epilogues (out == resid, fp32) push the term they add with
+// cp.reduce.async.bulk from a per-thread row buffer: the residual is never read, the adds happen in L2.
+template <int BN, bool LNF = false, bool PAIR = false, int EPI_MODE = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   using namespace sm100;
   using Cfg = TcCfg<BN>;
+  constexpr bool STAGED = EPI_MODE == 1, RED = EPI_MODE == 2;
   static_assert(!(LNF && PAIR), "LayerNorm fusion and CTA pairs both claim the cluster");
-  static_assert(!(LNF && STAGED), "the LayerNorm-fused kernel has no room for the staging tiles");
-  constexpr int STAGES = PAIR ? Cfg::PAIR_STAGES : Cfg::STAGES;
+  static_assert(!(LNF && EPI_MODE != 0) && !(PAIR && EPI_MODE != 0), "epilogue modes are built for the plain single-CTA kernel");
+  constexpr int STAGES = PAIR ? Cfg::PAIR_STAGES : RED ? Cfg::RED_STAGES : Cfg::STAGES;
   constexpr int STAGE_BYTES = PAIR ? Cfg::PAIR_STAGE_BYTES : Cfg::STAGE_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -128,8 +139,9 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       [[maybe_unused]] int tile_i = 0;
       const uint32_t full0 = PAIR ? mapa_shared(smem_u32(full_bar), 0) : 0u;      // the leader's full barriers, as seen from this CTA
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_i) {
-        const int m_blk = LNF ? tile : PAIR ? 2 * (tile % num_pm) + pair_rank : tile % p.num_m_tiles;
-        const int n_blk = LNF ? my_rank : tile / num_pm;
+        const int t_m = p.n_fast ? tile / p.num_n_tiles : tile % num_pm, t_n = p.n_fast ? tile % p.num_n_tiles : tile / num_pm;
+        const int m_blk = LNF ? tile : PAIR ? 2 * t_m + pair_rank : t_m;
+        const int n_blk = LNF ? my_rank : t_n;
         [[maybe_unused]] long long w_empty = 0;
         int x0 = 0, y0 = 0, b0 = 0;
         if (p.mode == 1) {
@@ -227,8 +239,9 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     [[maybe_unused]] const bool tr = (warp == 4 && lane == 0);
     const uint32_t tmem_empty0 = PAIR ? mapa_shared(smem_u32(tmem_empty), 0) : 0u;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_i) {
-      const int m_blk = LNF ? tile : PAIR ? 2 * (tile % num_pm) + pair_rank : tile % p.num_m_tiles;
-      const int n_blk = LNF ? my_rank : tile / num_pm;
+      const int t_m = p.n_fast ? tile / p.num_n_tiles : tile % num_pm, t_n = p.n_fast ? tile % p.num_n_tiles : tile / num_pm;
+      const int m_blk = LNF ? tile : PAIR ? 2 * t_m + pair_rank : t_m;
+      const int n_blk = LNF ? my_rank : t_n;
       int64_t row; bool valid;
       if (p.mode == 0) {
         row = (int64_t)m_blk * TC_BM + r_in_tile; valid = row < p.M;
@@ -247,7 +260,8 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       float (&rbuf)[64] = *reinterpret_cast<float (*)[64]>(&rb[0]);       // ... or this row's 64 values (direct)
       float ln_sum = 0.f, ln_sq = 0.f;
       // in flight while the MMA of this tile completes
-      if (stg) { if (pre_u) epi.load_resid_w(row, n_blk * BN + c_first * 64, valid, rb); }
+      if (RED) { }
+      else if (stg) { if (pre_u) epi.load_resid_w(row, n_blk * BN + c_first * 64, valid, rb); }
       else if (pre) epi.load_resid(row, n_blk * BN + c_first * 64, rbuf);
       if (tr) MMG_TR(4, MMG_CLK());
       mbar_wait(tmem_full + acc, acc_phase);
@@ -271,7 +285,24 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
           released = true;
         }
         const int col0 = n_blk * BN + c * 64;
-        if (STAGED && col0 < p.N && stg) {
+        if (RED && col0 < p.N) {
+          if (valid) {
+            epi.resid_term(col0, v);
+            float* gdst = reinterpret_cast<float*>(epi.p.out) + row * epi.p.ldo + col0;
+            const uint32_t sbuf = smem_u32(smem + STAGES * STAGE_BYTES + 256) + (uint32_t)(threadIdx.x - 128) * Cfg::RED_ROW_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              bulk_wait_read0();                        // this thread's previous push has left the row buffer
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(sbuf + 16u * j), "f"(v[32 * h + 4 * j]), "f"(v[32 * h + 4 * j + 1]),
+                             "f"(v[32 * h + 4 * j + 2]), "f"(v[32 * h + 4 * j + 3]) : "memory");
+              fence_proxy_async();                      // generic-proxy writes -> visible to the bulk (async-proxy) read
+              bulk_reduce_add_f32(gdst + 32 * h, sbuf, 128);
+              bulk_commit();
+            }
+          }
+        } else if (STAGED && col0 < p.N && stg) {
           epi.fuse_resid_w(col0, v, rb);
           const int cn = col0 + c_step * 64;
           if (c + c_step < BN / 64 && cn < p.N) epi.load_resid_w(row, cn, valid, rb);          // next chunk's residual overlaps the stores
@@ -342,6 +373,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     }
   }
 
+  if (RED && warp >= 4) bulk_wait0();           // every pushed row has landed before the CTA (and its shared memory) goes away
   tc_fence_before();
   __syncthreads();
   if (LNF || PAIR) cluster_sync_all();          // no CTA may exit while its peer can still write its shared memory / read its operands
