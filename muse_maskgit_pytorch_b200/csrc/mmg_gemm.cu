@@ -135,7 +135,9 @@ static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_
   const mmg_epilogue_args& e = p.epi.p;
   const bool in_place = (p.epi.kind == MMG_EPI_LNFOLD_RESIDUAL || (p.epi.kind == MMG_EPI_RESIDUAL && e.act == 0)) && e.out_dtype == MMG_F32 &&
                         e.out == e.resid && e.ldo == e.ldr && (e.ldo % 4) == 0 && aligned16(e.out) && !e.ln_out;
-  if (in_place && red_forced != 0) {
+  if (in_place && red_forced != 0 && p.mode == 0) {
+    uint64_t od[2] = {(uint64_t)p.N, (uint64_t)p.M}; uint64_t os[1] = {(uint64_t)e.ldo * 4}; uint32_t ob[2] = {32, 32};
+    rc = make_tmap_f32(&p.tma_out, e.out, 2, od, os, ob); if (rc) return rc;
     switch (bn) { case 64: return launch_tc_red<64>(p, st); case 128: return launch_tc_red<128>(p, st); case 256: return launch_tc_red<256>(p, st); }
   }
   switch (bn) {
