@@ -49,6 +49,20 @@ static int launch_tc_red(const TcGemmParams& p, cudaStream_t st) {
   return MMG_OK;
 }
 
+// plain fp32 store through the per-warp tiles + TMA store (the logits GEMM)
+template <int BN>
+static int launch_tc_tstore(const TcGemmParams& p, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES_RED); });
+  if (attr_err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(tc_gemm_tstore<%d>): %s", BN, cudaGetErrorString(attr_err));
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  MMG_CUDA(launch_pdl(tc_gemm_kernel<BN, false, false, 3>, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES_RED, st, p));
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
 // LayerNorm-fused variant: clusters of two CTAs (column halves of the same rows), grid = 2 * min(#m-tiles, #SM / 2)
 template <int BN>
 static int launch_tc_lnf(const TcGemmParams& p, cudaStream_t st) {
@@ -130,6 +144,12 @@ static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_
   if (pair) return launch_tc_pair<256>(p, st);
   static const int staged_forced = [] { const char* e = getenv("MMG_GEMM_STAGED"); return e ? atoi(e) : -1; }();
   const bool plain_f32 = p.epi.kind == MMG_EPI_STORE && p.epi.p.out_dtype == MMG_F32;
+  static const int tstore_forced = [] { const char* e = getenv("MMG_GEMM_TSTORE"); return e ? atoi(e) : -1; }();
+  if (bn == 256 && tstore_forced != 0 && plain_f32 && p.mode == 0 && !p.epi.p.bias && p.epi.p.act == 0 && (p.epi.p.ldo % 4) == 0 && aligned16(p.epi.p.out)) {
+    uint64_t od[2] = {(uint64_t)p.N, (uint64_t)p.M}; uint64_t os[1] = {(uint64_t)p.epi.p.ldo * 4}; uint32_t ob[2] = {32, 32};
+    rc = make_tmap_f32(&p.tma_out, p.epi.p.out, 2, od, os, ob); if (rc) return rc;
+    return launch_tc_tstore<256>(p, st);
+  }
   if (bn == 256 && staged_forced != 0 && (plain_f32 || (staged_forced == 1 && p.epi.kind != MMG_EPI_CONVT_RGB))) return launch_tc_staged<256>(p, st);
   static const int red_forced = [] { const char* e = getenv("MMG_GEMM_RED"); return e ? atoi(e) : -1; }();
   const mmg_epilogue_args& e = p.epi.p;

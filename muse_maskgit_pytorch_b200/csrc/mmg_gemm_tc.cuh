@@ -79,12 +79,13 @@ template <int BN> struct TcCfg {
 // 32 x 32 tile and push it with ONE TMA reduction (cp.reduce.async.bulk.tensor .add): the residual is never read, the adds happen
 // in L2, and the L1 sees 8 conflict-free shared-memory stores per thread instead of 16 row-strided global accesses.
 // (Per-thread 128-byte bulk reductions were measured first: 52 -> 41 us on the wo GEMM, limited by the bulk-operation rate.)
+// EPI_MODE 3: plain fp32 outputs (no bias / activation; the logits GEMM) leave through the same tiles with a TMA store.
 template <int BN, bool LNF = false, bool PAIR = false, int EPI_MODE = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   using namespace sm100;
   using Cfg = TcCfg<BN>;
-  constexpr bool STAGED = EPI_MODE == 1, RED = EPI_MODE == 2;
+  constexpr bool STAGED = EPI_MODE == 1, RED = EPI_MODE == 2 || EPI_MODE == 3, RED_ADD = EPI_MODE == 2;   // 3: same tiles, plain TMA store
   static_assert(!(LNF && PAIR), "LayerNorm fusion and CTA pairs both claim the cluster");
   static_assert(!(LNF && EPI_MODE != 0) && !(PAIR && EPI_MODE != 0), "epilogue modes are built for the plain single-CTA kernel");
   constexpr int STAGES = PAIR ? Cfg::PAIR_STAGES : Cfg::STAGES;
@@ -287,7 +288,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         const int col0 = n_blk * BN + c * 64;
         if (RED && col0 < p.N) {
           // rows past M hold garbage here and are clipped by the tensor map; the tile layout is the TMA 128-byte swizzle
-          epi.resid_term(col0, v);
+          if (RED_ADD) epi.resid_term(col0, v);
           const uint32_t wtile = smem_u32(smem + STAGES * STAGE_BYTES + 1024) + (uint32_t)(warp - 4) * 4096u;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -299,7 +300,11 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
                            "f"(v[32 * h + 4 * j]), "f"(v[32 * h + 4 * j + 1]), "f"(v[32 * h + 4 * j + 2]), "f"(v[32 * h + 4 * j + 3]) : "memory");
             fence_proxy_async();                          // generic-proxy writes -> visible to the TMA (async-proxy) read
             __syncwarp();
-            if (lane == 0) { tma_reduce_add_2d(&p.tma_out, wtile, col0 + 32 * h, m_blk * TC_BM + quarter * 32); bulk_commit(); }
+            if (lane == 0) {
+              if (RED_ADD) tma_reduce_add_2d(&p.tma_out, wtile, col0 + 32 * h, m_blk * TC_BM + quarter * 32);
+              else tma_store_2d(&p.tma_out, wtile, col0 + 32 * h, m_blk * TC_BM + quarter * 32);
+              bulk_commit();
+            }
           }
         } else if (STAGED && col0 < p.N && stg) {
           epi.fuse_resid_w(col0, v, rb);

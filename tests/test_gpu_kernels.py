@@ -548,3 +548,26 @@ def test_critic_score(cfg_branch):
     ops().critic_score(xc.cuda(), xn.cuda() if cfg_branch else None, g.cuda(), w.cuda(), 0.25, 3.0, 0.6, sc, seed=1, seed_dev=seed_dev, step=4, row_offset=100)
     up = torch.tensor([float(philox.uniform_at(12, 4, 100 + r, 0xFFFFFFFF)) for r in range(rows)])
     assert (sc.cpu() - (want + (up - 0.5) * 0.6)).abs().max() < 1e-5
+
+
+def test_linear_wide_tiles_tma_epilogues():
+    """Shapes large enough for the 256-column tiles, whose fp32 epilogues leave through per-warp shared-memory tiles and TMA:
+    a plain store (the logits GEMM's path) with a ragged last row block, and the in-place residual as a TMA reduction
+    (x += a W^T with the adds performed in L2; the second call checks that nothing but the product is added)."""
+    bf = torch.bfloat16
+    M, N, K = 300, 25600, 64                      # 3 x 100 tiles, rows 256..299 of the last block only
+    a, w = rnd("wa", (M, K), bf), rnd("ww", (N, K), bf, std=K ** -0.5)
+    out = torch.full((M + 7, N), 7.0, device="cuda")
+    ops().linear(dev(a, bf), dev(w, bf), out[:M])
+    ok, msg = close(out[:M], a @ w.t(), 2e-4)
+    assert ok, msg
+    assert bool((out[M:] == 7.0).all()), "rows past M were written"
+    M, N, K = 2000, 5120, 64                      # 16 x 20 tiles
+    a, w, x = rnd("ra", (M, K), bf), rnd("rw", (N, K), bf, std=K ** -0.5), rnd("rx", (M, N))
+    xd = dev(x)
+    ops().linear(dev(a, bf), dev(w, bf), xd, epilogue=ops().EPI_RESIDUAL, resid=xd)
+    ok, msg = close(xd, x + a @ w.t(), 3e-4)
+    assert ok, msg
+    ops().linear(dev(a, bf), dev(w, bf), xd, epilogue=ops().EPI_RESIDUAL, resid=xd)
+    ok, msg = close(xd, x + 2 * (a @ w.t()), 5e-4)
+    assert ok, msg
