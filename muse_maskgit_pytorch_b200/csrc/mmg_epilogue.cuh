@@ -13,86 +13,11 @@ struct Epilogue {
   float rgb_acc[4];
   float st_a, st_b;         // GEGLU: partial (sum, sumsq) of this thread's outputs; LNFOLD: (mean, rstd) of the row
   int r_b, r_t;             // QKV: (batch, token) of the row; CONVT*: (batch, y * W + x)
-  // Tensor-core kernel only: this warp's 4 KB shared-memory staging tile.  One thread owns one output ROW, so a direct 32-byte
-  // store / load instruction touches 32 different 128-byte lines, and the L1 pipeline retires such an instruction at ~2 cycles per
-  // line: 16.7 B/clk/SM measured (scripts/stbench.cu), which made every epilogue the critical path of its tile.  Staged through
-  // this tile, each instruction covers 4 rows x 128 contiguous bytes (28 B/clk/SM stores, 38 B/clk/SM loads).  nullptr (CUDA-core
-  // kernel, LayerNorm-fused kernel): direct row-per-thread accesses.
-  uint4* ws = nullptr;
-
-  // ---- warp-collective coalesced row segments (every lane of the warp must call; ptr == nullptr -> this lane has nothing) -------
-  // lane writes NQ * 16 bytes (NQ = 8: 128 B, NQ = 4: 64 B) at ptr (16-byte aligned)
-  template <int NQ>
-  __device__ __forceinline__ void wstore(void* ptr, const uint4 (&d)[NQ]) const {
-    const int lane = threadIdx.x & 31;
-    constexpr int SH = NQ == 8 ? 0 : 1;          // NQ = 4: two 64-byte rows share one 128-byte bank line
-#pragma unroll
-    for (int j = 0; j < NQ; ++j) ws[lane * NQ + (j ^ ((lane >> SH) & (NQ - 1)))] = d[j];
-    const unsigned long long pa = reinterpret_cast<unsigned long long>(ptr);
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < NQ; ++j) {
-      const int r = (32 / NQ) * j + lane / NQ, c = lane % NQ;
-      const unsigned long long q = __shfl_sync(0xffffffffu, pa, r);
-      const uint4 t = ws[r * NQ + (c ^ ((r >> SH) & (NQ - 1)))];
-      if (q) *reinterpret_cast<uint4*>(q + c * 16) = t;
-    }
-    __syncwarp();
-  }
-  // coalesced load of every lane's 128-byte segment into registers in the TRANSPOSED arrangement (t[j] = 16-byte chunk lane % 8 of
-  // row 4 j + lane / 8); wload_finish turns it into the lane's own 128 bytes.  Split so the loads can be in flight under the MMA.
-  __device__ __forceinline__ void wload_issue(const void* ptr, uint4 (&t)[8]) const {
-    const int lane = threadIdx.x & 31;
-    const unsigned long long pa = reinterpret_cast<unsigned long long>(ptr);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const unsigned long long q = __shfl_sync(0xffffffffu, pa, 4 * j + (lane >> 3));
-      t[j] = q ? *reinterpret_cast<const uint4*>(q + (lane & 7) * 16) : make_uint4(0u, 0u, 0u, 0u);
-    }
-  }
-  __device__ __forceinline__ void wload_finish(const uint4 (&t)[8], uint4 (&mine)[8]) const {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { const int r = 4 * j + (lane >> 3), c = lane & 7; ws[r * 8 + (c ^ (r & 7))] = t[j]; }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) mine[j] = ws[lane * 8 + (j ^ (lane & 7))];
-    __syncwarp();
-  }
-  static __device__ __forceinline__ void pack32_f32(const float* v, uint4 (&d)[8]) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) d[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-  }
-  static __device__ __forceinline__ void pack64_bf16(const float* v, uint4 (&d)[8]) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) d[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-  }
-  // 64 accumulator columns of this lane's row -> dst (T = float: 256 B, T = bf16: 128 B); collective when staged
-  template <bool WS, typename T>
-  __device__ __forceinline__ void store64(T* dst, const float (&v)[64], bool valid) const {
-    if (WS) {
-      uint4 d[8];
-      if constexpr (sizeof(T) == 4) {
-        pack32_f32(v, d);      wstore<8>(valid ? (void*)dst : nullptr, d);
-        pack32_f32(v + 32, d); wstore<8>(valid ? (void*)(dst + 32) : nullptr, d);
-      } else {
-        pack64_bf16(v, d);     wstore<8>(valid ? (void*)dst : nullptr, d);
-      }
-    } else if (valid) {
-      Vec64<T>::store(dst, v);
-    }
-  }
-  template <bool WS>
-  __device__ __forceinline__ bool staged(const void* base, int64_t ld_elems, int esize) const {    // warp-uniform
-    return WS && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && ((ld_elems * esize) & 15) == 0;
-  }
-
-  template <bool WS, typename T>
-  __device__ __forceinline__ void store_n(T* dst, const float (&v)[64], int n, bool vec_ok, bool valid, bool stage_ok) const {
+  template <typename T>
+  static __device__ __forceinline__ void store_n(T* dst, const float (&v)[64], int n, bool vec_ok) {
     if (vec_ok && n == 64) {
-      if (WS && stage_ok) store64<WS>(dst, v, valid);
-      else if (valid) Vec64<T>::store(dst, v);
-    } else if (valid) {
+      Vec64<T>::store(dst, v);
+    } else {
 #pragma unroll
       for (int i = 0; i < 64; ++i) if (i < n) dst[i] = from_f<T>(v[i]);
     }
@@ -125,14 +50,9 @@ struct Epilogue {
   }
 
   // row: global output row (< M). col0: first accumulator column of this chunk (multiple of 64). nvalid: columns < N.
-  // valid == false: this lane's row is outside the matrix; it still takes part in the warp-collective staged stores.
-  // WS: the kernel gave this warp a staging tile (`ws`) -> coalesced stores; compiled out otherwise.
-  template <bool FAST, bool WS = false>
-  __device__ __forceinline__ void apply(int64_t row, int col0, float (&v)[64], int nvalid, bool valid = true) {
+  template <bool FAST>
+  __device__ __forceinline__ void apply(int64_t row, int col0, float (&v)[64], int nvalid) {
     const bool bf = (p.out_dtype == MMG_BF16);
-    const bool coll = WS && (kind == MMG_EPI_STORE || kind == MMG_EPI_RESIDUAL || kind == MMG_EPI_GEGLU || kind == MMG_EPI_GLU ||
-                                        kind == MMG_EPI_QKV || kind == MMG_EPI_CONVT);
-    if (!valid && !coll) return;
     switch (kind) {
       case MMG_EPI_LFQ_IDS: {
         const int bits = p.ln_width;                 // 3 * bits <= 64: columns [hi | mid | lo] of the split projection
@@ -182,7 +102,7 @@ struct Epilogue {
           for (int i = 0; i < 64; ++i) if (i < nvalid) v[i] += __ldg(p.bias + col0 + i);
         }
         const bool vec_ok = (nvalid == 64) && ((p.ldo & 7) == 0);
-        if (kind == MMG_EPI_RESIDUAL && valid) {
+        if (kind == MMG_EPI_RESIDUAL) {
           const bool rvec = vec_ok && ((p.ldr & 7) == 0);
           if (bf) {
             const bf16* r = reinterpret_cast<const bf16*>(p.resid) + row * p.ldr + col0;
@@ -208,8 +128,8 @@ struct Epilogue {
 #pragma unroll
           for (int i = 0; i < 64; ++i) v[i] = leaky01(v[i]);
         }
-        if (bf) store_n<WS>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col0, v, nvalid, vec_ok, valid, staged<WS>(p.out, p.ldo, 2));
-        else    store_n<WS>(reinterpret_cast<float*>(p.out) + row * p.ldo + col0, v, nvalid, vec_ok, valid, staged<WS>(p.out, p.ldo, 4));
+        if (bf) store_n(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col0, v, nvalid, vec_ok);
+        else    store_n(reinterpret_cast<float*>(p.out) + row * p.ldo + col0, v, nvalid, vec_ok);
         break;
       }
       case MMG_EPI_GEGLU:
@@ -231,13 +151,7 @@ struct Epilogue {
           }
         }
         const int oc = col0 >> 1;
-        if (bf && staged<WS>(p.out, p.ldo, 2)) {        // 32 bf16 = 64 B per row and chunk
-          uint4 q4[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) q4[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]), pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
-          wstore<4>(valid ? (void*)(reinterpret_cast<bf16*>(p.out) + row * p.ldo + oc) : nullptr, q4);
-        } else if (!valid) {
-        } else if (bf) {
+        if (bf) {
           bf16* d = reinterpret_cast<bf16*>(p.out) + row * p.ldo + oc;
           if ((p.ldo & 7) == 0) store32_bf16(d, o);
           else {
@@ -273,9 +187,9 @@ struct Epilogue {
 #pragma unroll
           for (int i = 0; i < 64; ++i) v[i] = v[i] * inv * sc[i];
         }
-        if (bf) { if (staged<WS>(dst, 64, 2)) store64<WS>(reinterpret_cast<bf16*>(dst) + off, v, valid); else if (valid) Vec64<bf16>::store(reinterpret_cast<bf16*>(dst) + off, v); }
-        else    { if (staged<WS>(dst, 64, 4)) store64<WS>(reinterpret_cast<float*>(dst) + off, v, valid); else if (valid) Vec64<float>::store(reinterpret_cast<float*>(dst) + off, v); }
-        if (valid && t == 0 && hc >= p.nq_heads) {              // learned null key / value -> key row 0 (muse_maskgit_pytorch.py:145-149)
+        if (bf) Vec64<bf16>::store(reinterpret_cast<bf16*>(dst) + off, v);
+        else    Vec64<float>::store(reinterpret_cast<float*>(dst) + off, v);
+        if (t == 0 && hc >= p.nq_heads) {              // learned null key / value -> key row 0 (muse_maskgit_pytorch.py:145-149)
           const void* nsrc = (hc < p.nq_heads + p.nk_heads) ? p.null_k : p.null_v;
           if (nsrc) {
             const int64_t noff = ((b * p.heads + h) * (int64_t)p.kv_rows) * 64;
@@ -302,8 +216,8 @@ struct Epilogue {
           const int64_t b = r_b; const int rem = r_t; const int y = rem / p.W, x = rem - y * p.W;
           const int64_t opix = (b * 2 * p.H + 2 * y + p.py) * (int64_t)(2 * p.W) + 2 * x + p.px;
           const bool vec_ok = (nvalid == 64) && ((p.ldo & 7) == 0);
-          if (bf) store_n<WS>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + col0, v, nvalid, vec_ok, valid, staged<WS>(p.out, p.ldo, 2));
-          else    store_n<WS>(reinterpret_cast<float*>(p.out) + opix * p.ldo + col0, v, nvalid, vec_ok, valid, staged<WS>(p.out, p.ldo, 4));
+          if (bf) store_n(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + col0, v, nvalid, vec_ok);
+          else    store_n(reinterpret_cast<float*>(p.out) + opix * p.ldo + col0, v, nvalid, vec_ok);
         } else {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -353,36 +267,6 @@ struct Epilogue {
 #pragma unroll
       for (int i = 0; i < 64; ++i) v[i] += __ldg(p.bias + col0 + i);
     }
-  }
-  // staged (coalesced) variants of the three calls above; collective, valid == false lanes contribute nothing
-  template <bool WS>
-  __device__ __forceinline__ bool resid_staged() const { return staged<WS>(p.resid, p.ldr, 4) && staged<WS>(p.out, p.ldo, 4); }
-  __device__ __forceinline__ void load_resid_w(int64_t row, int col0, bool valid, uint4 (&rb)[16]) const {
-    const float* src = reinterpret_cast<const float*>(p.resid) + row * p.ldr + col0;
-    uint4 (&lo)[8] = *reinterpret_cast<uint4 (*)[8]>(&rb[0]);
-    uint4 (&hi)[8] = *reinterpret_cast<uint4 (*)[8]>(&rb[8]);
-    wload_issue(valid ? (const void*)src : nullptr, lo);
-    wload_issue(valid ? (const void*)(src + 32) : nullptr, hi);
-  }
-  __device__ __forceinline__ void fuse_resid_w(int col0, float (&v)[64], const uint4 (&rb)[16]) const {
-    uint4 m[8];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      wload_finish(*reinterpret_cast<const uint4 (*)[8]>(&rb[8 * h]), m);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float r4[4] = {__uint_as_float(m[j].x), __uint_as_float(m[j].y), __uint_as_float(m[j].z), __uint_as_float(m[j].w)};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = 32 * h + 4 * j + e;
-          if (kind == MMG_EPI_LNFOLD_RESIDUAL) v[i] = fmaf(st_b, v[i] - st_a * __ldg(p.bias + col0 + i), r4[e]);
-          else v[i] += r4[e] + (p.bias ? __ldg(p.bias + col0 + i) : 0.f);
-        }
-      }
-    }
-  }
-  __device__ __forceinline__ void store_f32_w(int64_t row, int col0, const float (&v)[64], bool valid) const {
-    store64<true>(reinterpret_cast<float*>(p.out) + row * p.ldo + col0, v, valid);
   }
   __device__ __forceinline__ void load_out_f32(int64_t row, int col0, float (&v)[64]) const {
     Vec64<float>::load(reinterpret_cast<const float*>(p.out) + row * p.ldo + col0, v);

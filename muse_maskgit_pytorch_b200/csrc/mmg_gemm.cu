@@ -20,21 +20,6 @@ static int launch_tc(const TcGemmParams& p, cudaStream_t st) {
   return MMG_OK;
 }
 
-// staged-store variant (coalesced epilogue stores through shared memory): pays where the epilogue is nothing but a wide store,
-// i.e. fp32 outputs (the logits GEMM: tile period 11 250 -> 9 250 cycles); measured slower for the bf16 / residual epilogues
-template <int BN>
-static int launch_tc_staged(const TcGemmParams& p, cudaStream_t st) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES_STAGED); });
-  if (attr_err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(tc_gemm_staged<%d>): %s", BN, cudaGetErrorString(attr_err));
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  MMG_CUDA(launch_pdl(tc_gemm_kernel<BN, false, false, 1>, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES_STAGED, st, p));
-  MMG_LAUNCHED();
-  return MMG_OK;
-}
-
 // in-place reduction epilogue (x += A W^T through cp.reduce.async.bulk): the residual GEMMs of the transformer blocks
 template <int BN>
 static int launch_tc_red(const TcGemmParams& p, cudaStream_t st) {
@@ -142,7 +127,6 @@ static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; uint64_t str[1] = {(uint64_t)ldw * 2}; uint32_t box[2] = {TC_BK, (uint32_t)(pair ? bn / 2 : bn)};
   int rc = make_tmap_bf16(&p.tma_b, w, 2, dims, str, box); if (rc) return rc;
   if (pair) return launch_tc_pair<256>(p, st);
-  static const int staged_forced = [] { const char* e = getenv("MMG_GEMM_STAGED"); return e ? atoi(e) : -1; }();
   const bool plain_f32 = p.epi.kind == MMG_EPI_STORE && p.epi.p.out_dtype == MMG_F32;
   static const int tstore_forced = [] { const char* e = getenv("MMG_GEMM_TSTORE"); return e ? atoi(e) : -1; }();
   if (bn == 256 && tstore_forced != 0 && plain_f32 && p.mode == 0 && !p.epi.p.bias && p.epi.p.act == 0 && (p.epi.p.ldo % 4) == 0 && aligned16(p.epi.p.out)) {
@@ -150,7 +134,6 @@ static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_
     rc = make_tmap_f32(&p.tma_out, p.epi.p.out, 2, od, os, ob); if (rc) return rc;
     return launch_tc_tstore<256>(p, st);
   }
-  if (bn == 256 && staged_forced != 0 && (plain_f32 || (staged_forced == 1 && p.epi.kind != MMG_EPI_CONVT_RGB))) return launch_tc_staged<256>(p, st);
   static const int red_forced = [] { const char* e = getenv("MMG_GEMM_RED"); return e ? atoi(e) : -1; }();
   const mmg_epilogue_args& e = p.epi.p;
   const bool in_place = (p.epi.kind == MMG_EPI_LNFOLD_RESIDUAL || (p.epi.kind == MMG_EPI_RESIDUAL && e.act == 0)) && e.out_dtype == MMG_F32 &&

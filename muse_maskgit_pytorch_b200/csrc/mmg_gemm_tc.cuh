@@ -57,9 +57,7 @@ template <int BN> struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = TC_EPI_WARPS * 4096;    // one 32-row x 128-byte transpose tile per epilogue warp (mmg_epilogue.cuh)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int SMEM_BYTES_STAGED = SMEM_BYTES + STAGING_BYTES;
   // in-place reduction epilogue (EPI_MODE 2): one 32-row x 128-byte tile per epilogue warp (1024-byte aligned for the TMA swizzle)
   static constexpr int SMEM_BYTES_RED = STAGES * STAGE_BYTES + 1024 + 1024 + TC_EPI_WARPS * 4096;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -74,8 +72,10 @@ template <int BN> struct TcCfg {
 // CTAs that own the two column halves (N == 2 * BN) of the same 128 rows; per-row (sum, sumsq) partials cross through DSMEM.
 // PAIR: launched as clusters of two CTAs that form one tcgen05 CTA pair: a 256 x BN output tile per pair, the leader (rank 0) issues
 // the MMAs for both SMs, TMA completions of both CTAs are counted on the leader's barriers, MMA commits are multicast to both.
-// EPI_MODE 1 (STAGED): the epilogue warps own a shared-memory staging tile each and write their rows through it (coalesced;
-// mmg_epilogue.cuh).  EPI_MODE 2 (RED): in-place residual epilogues (out == resid, fp32) write the term they add into a per-warp
+// One thread owns one output ROW, so a direct 32-byte store / load touches 32 different 128-byte lines per instruction and the L1
+// pipeline retires it at ~2 cycles per line: 16.7 B/clk/SM measured (scripts/stbench.cu) — 7 850 cycles for a 128 KB fp32 tile whose
+// MMAs take ~4 100.  The fp32 epilogues therefore leave through shared memory and the TMA engine instead:
+// EPI_MODE 2 (RED): in-place residual epilogues (out == resid, fp32) write the term they add into a per-warp
 // 32 x 32 tile and push it with ONE TMA reduction (cp.reduce.async.bulk.tensor .add): the residual is never read, the adds happen
 // in L2, and the L1 sees 8 conflict-free shared-memory stores per thread instead of 16 row-strided global accesses.
 // (Per-thread 128-byte bulk reductions were measured first: 52 -> 41 us on the wo GEMM, limited by the bulk-operation rate.)
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   using namespace sm100;
   using Cfg = TcCfg<BN>;
-  constexpr bool STAGED = EPI_MODE == 1, RED = EPI_MODE == 2 || EPI_MODE == 3, RED_ADD = EPI_MODE == 2;   // 3: same tiles, plain TMA store
+  constexpr bool RED = EPI_MODE == 2 || EPI_MODE == 3, RED_ADD = EPI_MODE == 2;   // 3: same tiles, plain TMA store
   static_assert(!(LNF && PAIR), "LayerNorm fusion and CTA pairs both claim the cluster");
   static_assert(!(LNF && EPI_MODE != 0) && !(PAIR && EPI_MODE != 0), "epilogue modes are built for the plain single-CTA kernel");
   constexpr int STAGES = PAIR ? Cfg::PAIR_STAGES : Cfg::STAGES;
@@ -229,11 +229,9 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     const int half = (warp - 4) >> 2;             // 0: even 64-column chunks, 1: odd chunks
     const int r_in_tile = quarter * 32 + lane;
     Epilogue epi = p.epi;
-    epi.ws = STAGED ? reinterpret_cast<uint4*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 4) * 256 : nullptr;
     if (epi.kind == MMG_EPI_QKV) { epi.p.q_scale = s_scale; epi.p.k_scale = s_scale + 64; }
     const bool whole_row = (epi.kind == MMG_EPI_CONVT_RGB);      // needs every chunk of a row in one thread
     const bool prefetch_resid = epi.can_prefetch_resid();
-    const bool stg = STAGED && prefetch_resid && epi.template resid_staged<STAGED>();       // residual rows read and written through the staging tile (coalesced)
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t stats_phase = 0; int stats_buf = 0;
     [[maybe_unused]] int tile_i = 0;
@@ -255,15 +253,10 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       }
       const bool mine = !whole_row || half == 0;
       const int c_first = whole_row ? 0 : half, c_step = whole_row ? 1 : 2;
-      const bool pre_u = prefetch_resid && mine && (n_blk * BN + c_first * 64 < p.N) && c_first < BN / 64;     // warp-uniform
-      const bool pre = pre_u && valid;
-      uint4 rb[16];                                                        // the residual chunk: transposed 16-byte pieces (staged) ...
-      float (&rbuf)[64] = *reinterpret_cast<float (*)[64]>(&rb[0]);       // ... or this row's 64 values (direct)
+      const bool pre = !RED && prefetch_resid && valid && mine && (n_blk * BN + c_first * 64 < p.N) && c_first < BN / 64;
+      float rbuf[64];
       float ln_sum = 0.f, ln_sq = 0.f;
-      // in flight while the MMA of this tile completes
-      if (RED) { }
-      else if (stg) { if (pre_u) epi.load_resid_w(row, n_blk * BN + c_first * 64, valid, rb); }
-      else if (pre) epi.load_resid(row, n_blk * BN + c_first * 64, rbuf);
+      if (pre) epi.load_resid(row, n_blk * BN + c_first * 64, rbuf);      // in flight while the MMA of this tile completes
       if (tr) MMG_TR(4, MMG_CLK());
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
@@ -306,13 +299,6 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
               bulk_commit();
             }
           }
-        } else if (STAGED && col0 < p.N && stg) {
-          epi.fuse_resid_w(col0, v, rb);
-          const int cn = col0 + c_step * 64;
-          if (c + c_step < BN / 64 && cn < p.N) epi.load_resid_w(row, cn, valid, rb);          // next chunk's residual overlaps the stores
-          epi.store_f32_w(row, col0, v, valid);
-        } else if (STAGED && col0 < p.N && !prefetch_resid) {
-          epi.template apply<true, STAGED>(row, col0, v, 64, valid);
         } else if (valid && col0 < p.N) {
           if (prefetch_resid) {
             epi.fuse_resid(col0, v, rbuf);
