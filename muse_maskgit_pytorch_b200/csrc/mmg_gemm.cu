@@ -68,45 +68,48 @@ static int launch_tc_lnf(const TcGemmParams& p, cudaStream_t st) {
 }
 
 // CTA-pair variant (cta_group::2): clusters of two CTAs, one 256 x BN tile per pair and step
-template <int BN>
+template <int BN, int EPI_MODE = 0>
 static int launch_tc_pair(const TcGemmParams& p, cudaStream_t st) {
+  constexpr int SMEM = EPI_MODE ? TcCfg<BN>::PAIR_SMEM_BYTES_RED : TcCfg<BN>::PAIR_SMEM_BYTES;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   static int max_clusters = 0;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::PAIR_SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, false, true, EPI_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (attr_err != cudaSuccess) return;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * (num_sms() / 2)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<BN>::PAIR_SMEM_BYTES;
+    cfg.gridDim = dim3(2 * (num_sms() / 2)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = SMEM;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    attr_err = cudaOccupancyMaxActiveClusters(&max_clusters, tc_gemm_kernel<BN, false, true>, &cfg);
+    attr_err = cudaOccupancyMaxActiveClusters(&max_clusters, tc_gemm_kernel<BN, false, true, EPI_MODE>, &cfg);
   });
   if (attr_err != cudaSuccess || max_clusters < 1) return fail(MMG_ECUDA, "tc_gemm pair<%d> setup: %s (clusters %d)", BN, cudaGetErrorString(attr_err), max_clusters);
   const int tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<BN>::PAIR_SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  MMG_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, false, true>, p));
+  MMG_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, false, true, EPI_MODE>, p));
   MMG_LAUNCHED();
   return MMG_OK;
 }
 
-// CTA pairs (cta_group::2) cut the L2->SM operand traffic by a third and deepen the ring to six stages: -18 % on a tile with a long
-// K loop (8192^3: 79 650 -> 65 570 cycles per tile), which is where the operand feed is the limiter (the 3x3 convolutions of the
-// VAE, K = 9 * Cin).  The K = 512 transformer GEMMs are bound by their epilogues and get slower in lock-step pairs, so they stay on
-// single CTAs.  MMG_GEMM_PAIR = 0 / 1 forces the choice for A/B measurements.
-static bool use_pair(const TcGemmParams& p, int bn) {
+// CTA pairs (cta_group::2) cut the L2->SM operand traffic by a third and deepen the ring to six stages.  They win where the operand
+// feed is the limiter: long K loops (8192^3: 788 -> 732 us = 88 % of the measured cuBLAS rate; the VAE 3x3 convolutions, K = 9 Cin:
+// -10 %; FF2, K = 1408: 57 -> 51 us) and the logits GEMM (-1..5 %).  The K = 512 GEMMs with a register epilogue (QKV, GEGLU) and
+// the short residual GEMM get slower in lock-step pairs and stay on single CTAs.  MMG_GEMM_PAIR = 0 / 1 forces the choice.
+static bool use_pair(const TcGemmParams& p, int bn, int epi_mode) {
   static const int forced = [] { const char* e = getenv("MMG_GEMM_PAIR"); return e ? atoi(e) : -1; }();
   if (bn != 256 || forced == 0 || p.num_m_tiles < 2) return false;
   if (forced == 1) return true;
-  return p.mode == 1 && p.epi.kind != MMG_EPI_CONVT && p.epi.kind != MMG_EPI_CONVT_RGB && p.num_kb >= 64 &&
-         ((p.num_m_tiles + 1) / 2) * p.num_n_tiles >= 64;
+  if (((p.num_m_tiles + 1) / 2) * p.num_n_tiles < 64) return false;
+  if (epi_mode == 3) return true;
+  if (epi_mode == 2) return p.num_kb >= 16;
+  return p.num_kb >= 64 && p.epi.kind != MMG_EPI_CONVT && p.epi.kind != MMG_EPI_CONVT_RGB;
 }
 
 static int pick_bn(int64_t M_tiles, int64_t N, int epilogue) {
@@ -123,24 +126,23 @@ static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_
     static const int nfast_forced = [] { const char* e = getenv("MMG_GEMM_NFAST"); return e ? atoi(e) : -1; }();
     p.n_fast = nfast_forced >= 0 ? nfast_forced : ((int64_t)N * K * 2 <= (8 << 20) && p.num_n_tiles > 1 && p.num_n_tiles <= 16) ? 1 : 0;
   }
-  const bool pair = use_pair(p, bn);
-  uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; uint64_t str[1] = {(uint64_t)ldw * 2}; uint32_t box[2] = {TC_BK, (uint32_t)(pair ? bn / 2 : bn)};
-  int rc = make_tmap_bf16(&p.tma_b, w, 2, dims, str, box); if (rc) return rc;
-  if (pair) return launch_tc_pair<256>(p, st);
-  const bool plain_f32 = p.epi.kind == MMG_EPI_STORE && p.epi.p.out_dtype == MMG_F32;
-  static const int tstore_forced = [] { const char* e = getenv("MMG_GEMM_TSTORE"); return e ? atoi(e) : -1; }();
-  if (bn == 256 && tstore_forced != 0 && plain_f32 && p.mode == 0 && !p.epi.p.bias && p.epi.p.act == 0 && (p.epi.p.ldo % 4) == 0 && aligned16(p.epi.p.out)) {
-    uint64_t od[2] = {(uint64_t)p.N, (uint64_t)p.M}; uint64_t os[1] = {(uint64_t)p.epi.p.ldo * 4}; uint32_t ob[2] = {32, 32};
-    rc = make_tmap_f32(&p.tma_out, p.epi.p.out, 2, od, os, ob); if (rc) return rc;
-    return launch_tc_tstore<256>(p, st);
-  }
-  static const int red_forced = [] { const char* e = getenv("MMG_GEMM_RED"); return e ? atoi(e) : -1; }();
   const mmg_epilogue_args& e = p.epi.p;
   const bool in_place = (p.epi.kind == MMG_EPI_LNFOLD_RESIDUAL || (p.epi.kind == MMG_EPI_RESIDUAL && e.act == 0)) && e.out_dtype == MMG_F32 &&
-                        e.out == e.resid && e.ldo == e.ldr && (e.ldo % 4) == 0 && aligned16(e.out) && !e.ln_out;
-  if (in_place && red_forced != 0 && p.mode == 0) {
+                        e.out == e.resid && e.ldo == e.ldr && (e.ldo % 4) == 0 && aligned16(e.out) && !e.ln_out && p.mode == 0;
+  const bool plain_f32 = p.epi.kind == MMG_EPI_STORE && e.out_dtype == MMG_F32 && p.mode == 0 && !e.bias && e.act == 0 && (e.ldo % 4) == 0 && aligned16(e.out);
+  static const int red_forced = [] { const char* ev = getenv("MMG_GEMM_RED"); return ev ? atoi(ev) : -1; }();
+  static const int tstore_forced = [] { const char* ev = getenv("MMG_GEMM_TSTORE"); return ev ? atoi(ev) : -1; }();
+  const int epi_mode = (in_place && red_forced != 0) ? 2 : (plain_f32 && tstore_forced != 0 && bn == 256) ? 3 : 0;
+  const bool pair = use_pair(p, bn, epi_mode);
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; uint64_t str[1] = {(uint64_t)ldw * 2}; uint32_t box[2] = {TC_BK, (uint32_t)(pair ? bn / 2 : bn)};
+  int rc = make_tmap_bf16(&p.tma_b, w, 2, dims, str, box); if (rc) return rc;
+  if (epi_mode) {
     uint64_t od[2] = {(uint64_t)p.N, (uint64_t)p.M}; uint64_t os[1] = {(uint64_t)e.ldo * 4}; uint32_t ob[2] = {32, 32};
     rc = make_tmap_f32(&p.tma_out, e.out, 2, od, os, ob); if (rc) return rc;
+  }
+  if (pair) return epi_mode == 2 ? launch_tc_pair<256, 2>(p, st) : epi_mode == 3 ? launch_tc_pair<256, 3>(p, st) : launch_tc_pair<256>(p, st);
+  if (epi_mode == 3) return launch_tc_tstore<256>(p, st);
+  if (epi_mode == 2) {
     switch (bn) { case 64: return launch_tc_red<64>(p, st); case 128: return launch_tc_red<128>(p, st); case 256: return launch_tc_red<256>(p, st); }
   }
   switch (bn) {

@@ -66,6 +66,7 @@ template <int BN> struct TcCfg {
   static constexpr int PAIR_STAGES = 6;
   static constexpr int PAIR_STAGE_BYTES = A_BYTES + B_BYTES / 2;
   static constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256;
+  static constexpr int PAIR_SMEM_BYTES_RED = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 1024 + TC_EPI_WARPS * 4096;
 };
 
 // LNF: the epilogue additionally emits LayerNorm(out row) as bf16 (see mmg_epilogue_args::ln_out).  Launched as clusters of two
@@ -87,7 +88,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   using Cfg = TcCfg<BN>;
   constexpr bool RED = EPI_MODE == 2 || EPI_MODE == 3, RED_ADD = EPI_MODE == 2;   // 3: same tiles, plain TMA store
   static_assert(!(LNF && PAIR), "LayerNorm fusion and CTA pairs both claim the cluster");
-  static_assert(!(LNF && EPI_MODE != 0) && !(PAIR && EPI_MODE != 0), "epilogue modes are built for the plain single-CTA kernel");
+  static_assert(!(LNF && EPI_MODE != 0), "the LayerNorm-fused kernel has no room for the epilogue tiles");
   constexpr int STAGES = PAIR ? Cfg::PAIR_STAGES : Cfg::STAGES;
   constexpr int STAGE_BYTES = PAIR ? Cfg::PAIR_STAGE_BYTES : Cfg::STAGE_BYTES;
 
