@@ -284,6 +284,55 @@ typedef struct {
 } mmg_vq_decode_codes_args;
 int mmg_vq_decode_codes(const mmg_vq_decode_codes_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Composite entry points: the launch sequences of one FeedForward and of one whole decode step, for hosts that want one call
+ * per step.  They only issue the entry points above on `stream` (no allocation, no host sync, CUDA-graph capturable).
+ * ---------------------------------------------------------------------------------------------- */
+/* FeedForward of a block on `rows` rows, in place on the fp32 residual stream (muse_maskgit_pytorch.py:72-89), bf16 operands:
+ *   xn = LN(x [+ add on rows >= add_from, written back]) * ln_gamma;  h = gate * gelu_erf(xn W1^T);  x += LN(h) * gamma_inner W2^T
+ * (the inner LayerNorm is folded through the second product: w2f = W2 * gamma_inner, cvec = rowsum(w2f), MMG_EPI_LNFOLD_RESIDUAL). */
+typedef struct {
+  float* x; int64_t rows; int32_t dim, F, Fp;     /* x [rows, dim]; F = inner width int(dim*mult*2/3), Fp = F padded to a multiple of 64 */
+  const float* ln_gamma;                          /* [dim]                                                                  */
+  const void* w1;                                 /* [2*Fp, dim] bf16, rows interleaved in blocks of 32: [x(32) | gate(32)] */
+  const void* w2f; const float* cvec;             /* [dim, Fp] bf16, [dim]                                                  */
+  const float* add; int64_t add_from;             /* optional [dim] constant (to_out(null_v) of an all-masked cross-attention) */
+  void* xn; void* h; float* stats;                /* workspace: [rows, dim] bf16, [rows, Fp] bf16, [rows, 2] fp32            */
+} mmg_ff_geglu_args;
+int mmg_ff_geglu(const mmg_ff_geglu_args* a, void* stream);
+
+/* One step of MaskGit.generate (muse_maskgit_pytorch.py:556-609) for the default path (bf16, no token critic, no self-conditioning):
+ * re-mask -> embed -> depth x [self-attention, cross-attention, FeedForward] over `branches` copies of the batch (1, or 2 = cond + null
+ * CFG; the first `live_branches` attend to the context, the others take the constant to_out(null_v)) -> final LayerNorm + CFG combine
+ * on the masked rows -> logits GEMM -> top-k / gumbel argmax / confidence.  ids / scores / masked_pos are updated in place. */
+typedef struct {
+  const float* ln_gamma; const void* w_qkv;       /* self: [3*heads*64, dim]; cross: [heads*64, dim] (q only)                */
+  const void* w_out;                              /* [dim, heads*64]                                                         */
+  const float* q_scale; const float* k_scale;     /* [64]; k_scale, null_k, null_v: self-attention only                      */
+  const void* null_k; const void* null_v;         /* [heads, 64] bf16: l2norm(null_k)*k_scale, null_v                        */
+  float logit_bound; int32_t _pad;                /* max_i |q_scale_i k_scale_i| (+ slack), see mmg_attention_args           */
+} mmg_attn_weights;
+typedef struct {
+  mmg_attn_weights self_attn, cross_attn;
+  const void* ctx_k; const void* ctx_v;           /* this layer's context K/V [live*b*heads, ctx_alloc, 64] bf16 (null key at row 0), computed
+                                                     once per generate() with mmg_linear + MMG_EPI_QKV                       */
+  const float* cross_null_out;                    /* [dim] to_out(null_v)                                                    */
+  const float* ff_ln_gamma; const void* ff_w1; const void* ff_w2f; const float* ff_cvec;
+} mmg_layer_weights;
+typedef struct {
+  int32_t depth, dim, heads, n, V, F, Fp, b, branches, live_branches;
+  const mmg_layer_weights* layers;                /* HOST array [depth]                                                      */
+  const float* tok_emb; const float* pos_emb; const float* final_gamma; const void* w_logits;   /* fp32, fp32, fp32, [V, dim] bf16 */
+  const uint8_t* ctx_key_mask; int32_t ctx_keys, ctx_alloc;   /* [live*b, ctx_keys] (1 = attend); keys incl. the null key = ctx_keys + 1 */
+  int64_t* ids; float* scores; int32_t* masked_pos; int64_t mask_id;     /* [b, n], [b, n], [b, n] */
+  int32_t num_masked, k_keep, step; float temperature, cond_scale; int32_t _pad;
+  const float* u; uint64_t seed; const uint64_t* seed_dev; int64_t row_offset;   /* noise: see mmg_logits_sample_args        */
+  void* workspace; uint64_t workspace_bytes;      /* >= mmg_decode_step_workspace_bytes(...), 256-byte aligned, ZERO-INITIALISED once by
+                                                     the caller (the padding rows of the self-attention K/V stay zero)        */
+} mmg_decode_step_args;
+uint64_t mmg_decode_step_workspace_bytes(int32_t b, int32_t branches, int32_t n, int32_t dim, int32_t heads, int32_t Fp, int32_t V, int32_t max_masked);
+int mmg_decode_step(const mmg_decode_step_args* a, void* stream);
+
 /* dtype conversion / layout helpers used by the host mirror */
 typedef struct { const void* src; void* dst; int64_t n; int32_t src_dtype, dst_dtype; } mmg_cast_args;
 int mmg_cast(const mmg_cast_args* a, void* stream);

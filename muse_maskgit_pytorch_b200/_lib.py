@@ -88,6 +88,29 @@ class CriticScoreArgs(C.Structure):
                 ("step", i32), ("rng_mode", i32), ("aten_offset", u64), ("aten_offset_dev", vp), ("aten_stride", C.c_uint32), ("_pad", i32)]
 
 
+class FfGegluArgs(C.Structure):
+    _fields_ = [("x", vp), ("rows", i64), ("dim", i32), ("F", i32), ("Fp", i32), ("ln_gamma", vp), ("w1", vp), ("w2f", vp), ("cvec", vp),
+                ("add", vp), ("add_from", i64), ("xn", vp), ("h", vp), ("stats", vp)]
+
+
+class AttnWeights(C.Structure):
+    _fields_ = [("ln_gamma", vp), ("w_qkv", vp), ("w_out", vp), ("q_scale", vp), ("k_scale", vp), ("null_k", vp), ("null_v", vp),
+                ("logit_bound", f32), ("_pad", i32)]
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [("self_attn", AttnWeights), ("cross_attn", AttnWeights), ("ctx_k", vp), ("ctx_v", vp), ("cross_null_out", vp),
+                ("ff_ln_gamma", vp), ("ff_w1", vp), ("ff_w2f", vp), ("ff_cvec", vp)]
+
+
+class DecodeStepArgs(C.Structure):
+    _fields_ = [("depth", i32), ("dim", i32), ("heads", i32), ("n", i32), ("V", i32), ("F", i32), ("Fp", i32), ("b", i32), ("branches", i32),
+                ("live_branches", i32), ("layers", C.POINTER(LayerWeights)), ("tok_emb", vp), ("pos_emb", vp), ("final_gamma", vp), ("w_logits", vp),
+                ("ctx_key_mask", vp), ("ctx_keys", i32), ("ctx_alloc", i32), ("ids", vp), ("scores", vp), ("masked_pos", vp), ("mask_id", i64),
+                ("num_masked", i32), ("k_keep", i32), ("step", i32), ("temperature", f32), ("cond_scale", f32), ("_pad", i32),
+                ("u", vp), ("seed", u64), ("seed_dev", vp), ("row_offset", i64), ("workspace", vp), ("workspace_bytes", u64)]
+
+
 class LfqEncodeArgs(C.Structure):
     _fields_ = [("x", vp), ("dtype", i32), ("w_in", vp), ("b_in", vp), ("ids", vp), ("T", i64), ("D", i32), ("bits", i32)]
 
@@ -110,8 +133,9 @@ EXPORTS = {
     "mmg_attention": AttentionArgs, "mmg_remask": RemaskArgs, "mmg_final_embed": FinalEmbedArgs,
     "mmg_logits_sample": LogitsSampleArgs, "mmg_vq_lfq_encode": LfqEncodeArgs, "mmg_vq_l2_argmin": L2ArgminArgs,
     "mmg_vq_decode_codes": DecodeCodesArgs, "mmg_cast": CastArgs, "mmg_critic_score": CriticScoreArgs,
+    "mmg_ff_geglu": FfGegluArgs, "mmg_decode_step": DecodeStepArgs,
 }
-PLAIN_EXPORTS = ("mmg_version", "mmg_last_error", "mmg_launch_count", "mmg_sizeof")
+PLAIN_EXPORTS = ("mmg_version", "mmg_last_error", "mmg_launch_count", "mmg_sizeof", "mmg_decode_step_workspace_bytes")
 
 _lib = None
 
@@ -137,7 +161,9 @@ def lib():
         l.mmg_launch_count.restype = C.c_int64
         l.mmg_sizeof.argtypes = [C.c_char_p]
         l.mmg_sizeof.restype = C.c_int
-        for name, st in list(EXPORTS.items()) + [("mmg_epilogue", EpilogueArgs)]:
+        l.mmg_decode_step_workspace_bytes.argtypes = [i32] * 8
+        l.mmg_decode_step_workspace_bytes.restype = u64
+        for name, st in list(EXPORTS.items()) + [("mmg_epilogue", EpilogueArgs), ("mmg_attn_weights", AttnWeights), ("mmg_layer_weights", LayerWeights)]:
             if l.mmg_sizeof(name.encode()) != C.sizeof(st):
                 raise MMGError(f"ABI mismatch for {name}: C {l.mmg_sizeof(name.encode())} vs ctypes {C.sizeof(st)}")
         _lib = l

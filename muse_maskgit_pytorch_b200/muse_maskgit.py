@@ -8,6 +8,7 @@ The nn.Modules here only HOLD parameters under the reference's state_dict keys (
 Both CFG branches of a decode step run as one batch of 2B sequences; the null branch's cross-attention is the
 constant to_out(null_v) (every text key masked -> softmax puts weight exactly 1 on the null key).
 """
+import ctypes
 import math
 import os
 from functools import partial
@@ -17,7 +18,7 @@ from typing import Callable, List, Optional
 import torch
 from torch import nn
 
-from . import ops
+from . import ops, _lib
 from .t5 import t5_encode_text, get_encoded_dim, DEFAULT_T5_NAME
 from .vqgan_vae import VQGanVAE
 
@@ -489,6 +490,7 @@ class MaskGit(nn.Module):
         self.sampler_rng = "mmg"
         self.global_batch = None            # "aten" + batch sharding: size of the whole batch the reference would have drawn noise for
         self.use_cuda_graph = True
+        self.use_native_step = False        # True: one mmg_decode_step call per step (the same launch sequence issued from C++)
         self._graphs = {}
         self.row_offset = 0                 # global index of this shard's first sequence (multi-GPU batch sharding)
 
@@ -555,7 +557,7 @@ class MaskGit(nn.Module):
         # ---- whole-call CUDA graph: 18 decode steps + VAE decode replayed as one launch (no per-kernel host work) ----
         key = (b, tuple(text_embeds.shape), text_embeds.dtype, None if cond_images is None else tuple(cond_images.shape), fmap_size,
                float(temperature), float(topk_filter_thres), int(timesteps), float(cond_scale), int(self.row_offset), tr.precision, self.vae.precision,
-               use_critic, float(critic_noise_scale), bool(can_remask_prev_masked), None if aten is None else aten["key"])
+               use_critic, float(critic_noise_scale), bool(can_remask_prev_masked), None if aten is None else aten["key"], bool(self.use_native_step))
         pack_ids = lambda: (id(tr._pack), id(self.vae._pack), id(self.cond_vae._pack), id(critic_net._pack) if critic_net is not None else 0,
                             id(self.token_critic._head_cache) if isinstance(self.token_critic, SelfCritic) else 0)
         entry = self._graphs.get(key)
@@ -584,6 +586,39 @@ class MaskGit(nn.Module):
         graph.replay()
         images, ids = out_images.clone(), out_ids.clone()
         return (images, ids) if return_ids else images
+
+    def _native_step_setup(self, ctx, P, b, n, nb, max_masked, V, device):
+        """Argument block of mmg_decode_step for this generate(): the packed weights and the per-call context as raw pointers, plus the
+        zero-initialised workspace.  Everything referenced is kept alive by the returned dict (and by `P` / `ctx`)."""
+        tr = self.transformer
+        tb = tr.transformer_blocks
+        depth = len(P["layers"])
+        live = sum(1 for m in ctx["all_masked"][:nb] if not m)
+        assert ctx["all_masked"][:nb] == [False] * live + [True] * (nb - live), "live CFG branches must come first"
+        layers = (_lib.LayerWeights * depth)()
+        for li, lay in enumerate(P["layers"]):
+            sa, ca, ff, lw = lay["sa"], lay["ca"], lay["ff"], layers[li]
+            lw.self_attn.ln_gamma = sa["g"].data_ptr(); lw.self_attn.w_qkv = sa["wqkv"].data_ptr(); lw.self_attn.w_out = sa["wo"].data_ptr()
+            lw.self_attn.q_scale = sa["qs"].data_ptr(); lw.self_attn.k_scale = sa["ks"].data_ptr()
+            lw.self_attn.null_k = sa["nk"].data_ptr(); lw.self_attn.null_v = sa["nv"].data_ptr(); lw.self_attn.logit_bound = sa["bound"]
+            lw.cross_attn.ln_gamma = ca["g"].data_ptr(); lw.cross_attn.w_qkv = ca["wq"].data_ptr(); lw.cross_attn.w_out = ca["wo"].data_ptr()
+            lw.cross_attn.q_scale = ca["qs"].data_ptr(); lw.cross_attn.logit_bound = ca["bound"]
+            kc, vc = ctx["kv"][li]
+            lw.ctx_k = kc.data_ptr(); lw.ctx_v = vc.data_ptr(); lw.cross_null_out = ca["null_out"].data_ptr()
+            lw.ff_ln_gamma = ff["g0"].data_ptr(); lw.ff_w1 = ff["w1"].data_ptr(); lw.ff_w2f = ff["w2f"].data_ptr(); lw.ff_cvec = ff["cvec"].data_ptr()
+        ff0 = P["layers"][0]["ff"]
+        assert all(l["ff"]["Fp"] == ff0["Fp"] and l["ff"]["F"] == ff0["F"] for l in P["layers"])
+        nbytes = int(_lib.lib().mmg_decode_step_workspace_bytes(b, nb, n, tr.dim, tb.heads, ff0["Fp"], V, max_masked))
+        ws = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+        a = _lib.DecodeStepArgs()
+        a.depth = depth; a.dim = tr.dim; a.heads = tb.heads; a.n = n; a.V = V; a.F = ff0["F"]; a.Fp = ff0["Fp"]; a.b = b
+        a.branches = nb; a.live_branches = live
+        a.layers = ctypes.cast(layers, ctypes.POINTER(_lib.LayerWeights))
+        a.tok_emb = P["tok"].data_ptr(); a.pos_emb = P["pos"].data_ptr(); a.final_gamma = P["gf"].data_ptr(); a.w_logits = P["wlog"].data_ptr()
+        a.ctx_key_mask = ctx["key_mask"].data_ptr(); a.ctx_keys = ctx["m"]; a.ctx_alloc = ctx["kv"][0][0].shape[1]
+        a.mask_id = self.mask_id
+        a.workspace = ws.data_ptr(); a.workspace_bytes = nbytes
+        return dict(args=a, layers=layers, ws=ws, ctx=ctx, P=P)
 
     def _aten_plan(self, device, b, n, V, timesteps, use_critic):
         """Offsets of the reference's uniform_ calls in torch's CUDA Philox stream (one (b, n, V) gumbel draw, then one (b, n) critic
@@ -623,10 +658,14 @@ class MaskGit(nn.Module):
         masked_pos = torch.empty((b, n), dtype=torch.int32, device=device)
         k_keep = math.ceil((1 - topk_filter_thres) * V)                        # muse_maskgit_pytorch.py:414
         sched = self.mask_schedule(n, timesteps)
-        e = torch.empty((b * n, tr.dim), device=device, dtype=adt)
         bn = b * n
+        native = None
+        if (self.use_native_step and adt == torch.bfloat16 and not self.self_cond and not use_critic and not score_all and aten is None
+                and all("w2f" in l["ff"] for l in P["layers"])):
+            native = self._native_step_setup(ctx, P, b, n, nb, max(sched), V, device)
         rows_max = n if score_all else max(sched)
-        logits = torch.empty((b * rows_max, V), device=device, dtype=torch.float32)
+        e = torch.empty((b * n, tr.dim), device=device, dtype=adt) if native is None else None
+        logits = torch.empty((b * rows_max, V), device=device, dtype=torch.float32) if native is None else None
         all_pos = torch.arange(n, dtype=torch.int32, device=device).repeat(b, 1).contiguous() if score_all else None
         sc_embed = torch.empty((bn, tr.dim), device=device, dtype=torch.float32) if self.self_cond else None
         # token critic (muse_maskgit_pytorch.py:535-538, 590-600): a second stack over the freshly filled ids scores EVERY position
@@ -642,6 +681,17 @@ class MaskGit(nn.Module):
                 assert whead is not None, "token_critic must have dim_out == 1"
             gcrit = cnet._packed()["gf"]
         for step, (num_masked, steps_until_x0) in enumerate(zip(sched, reversed(range(timesteps)))):
+            if native is not None:
+                u = None
+                if self.sampler_noise_fn is not None:
+                    u = self.sampler_noise_fn(step, (b, n, V)).to(device=device, dtype=torch.float32).contiguous()
+                a = native["args"]
+                a.ids = ids.data_ptr(); a.scores = scores.data_ptr(); a.masked_pos = masked_pos.data_ptr()
+                a.num_masked = num_masked; a.k_keep = k_keep; a.step = step
+                a.temperature = float(temperature * (steps_until_x0 / timesteps)); a.cond_scale = float(cond_scale)
+                a.u = None if u is None else u.data_ptr(); a.seed = 0; a.seed_dev = self._seed_dev.data_ptr(); a.row_offset = self.row_offset * n
+                _lib.call("mmg_decode_step", a)
+                continue
             ops.remask(ids, scores, masked_pos, num_masked, self.mask_id)
             x = tr._run_blocks(ids, ctx, nb, sc_embed if (self.self_cond and step > 0) else None)
             if self.self_cond:                                                 # embed of the conditional forward, fed back next step (:574)

@@ -186,6 +186,18 @@ def critic_score(x_cond, x_null, gamma, w, bias, cond_scale, noise_mul, scores, 
     return scores
 
 
+def ff_geglu(x, ln_gamma, w1, w2f, cvec, F, xn, h, stats, add=None, add_from=0):
+    """x += FeedForward(x) in place (one C call = LayerNorm + GEGLU GEMM + LN-folded GEMM); bf16 operands, fp32 residual stream."""
+    a = L.FfGegluArgs()
+    a.x = _chk(x).data_ptr(); a.rows, a.dim = x.shape; a.F = F; a.Fp = w2f.shape[1]
+    a.ln_gamma = ln_gamma.data_ptr(); a.w1 = _chk(w1).data_ptr(); a.w2f = _chk(w2f).data_ptr(); a.cvec = cvec.data_ptr()
+    a.add = L.ptr(add); a.add_from = add_from
+    a.xn = _chk(xn).data_ptr(); a.h = _chk(h).data_ptr(); a.stats = stats.data_ptr()
+    assert x.dtype == torch.float32 and w1.dtype == torch.bfloat16 and w1.shape[0] == 2 * a.Fp and tuple(h.shape) == (a.rows, a.Fp)
+    L.call("mmg_ff_geglu", a)
+    return x
+
+
 def vq_lfq_encode(x, w_in, b_in, ids, bits):
     a = L.LfqEncodeArgs()
     a.x = _chk(x).data_ptr(); a.dtype = L.dt(x); a.w_in = L.ptr(w_in); a.b_in = L.ptr(b_in); a.ids = ids.data_ptr()

@@ -11,7 +11,7 @@ def test_library_exports_header_symbols():
     from muse_maskgit_pytorch_b200 import build, _lib
     build.build()
     header = open(os.path.join(ROOT, "include", "mmg.h")).read()
-    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(mmg_[a-z0-9_]+)\s*\(", header, re.M))
+    declared = set(re.findall(r"^\s*(?:int|int64_t|uint64_t|const char\*)\s+(mmg_[a-z0-9_]+)\s*\(", header, re.M))
     assert {"mmg_linear", "mmg_attention", "mmg_logits_sample", "mmg_vq_lfq_encode", "mmg_vq_l2_argmin", "mmg_conv2d",
             "mmg_conv_transpose2d", "mmg_remask", "mmg_version"} <= declared
     lib = ctypes.CDLL(_lib.LIB_PATH)

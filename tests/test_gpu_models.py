@@ -322,3 +322,68 @@ def test_muse_cascade_runs_on_device():
     lo2 = base.generate(["a", "b"], timesteps=6, cond_scale=3., temperature=1.)
     hi2 = sup.generate(["a", "b"], cond_images=lo2, timesteps=6, cond_scale=3., temperature=1.)
     assert torch.equal(lo, lo2) and torch.equal(hi, hi2)
+
+
+@pytest.mark.parametrize("superres", [False, True], ids=["base", "superres"])
+def test_decode_step_c_abi_equals_python_orchestration(superres):
+    """mmg_decode_step (the whole decode step issued from C++: one call per step) launches exactly what the Python mirror launches
+    call by call: same tokens and pixels, eager and under the whole-call CUDA graph, with injected noise and with Philox."""
+    mg = make_maskgit("bf16", superres=superres)
+    nb_ = 2 if superres else 3
+    te = util.text_embeds("g4.te", 3, 8, 128, 14).cuda()[:nb_]
+    mg.transformer.encode_text = lambda texts: te[:len(texts)]
+    kw = dict(timesteps=8)
+    if superres:
+        kw["cond_images"] = torch.from_numpy(synth.uniform("g5.cond", (2, 3, 16, 16), 15)).cuda()
+    outs = {}
+    for native in (False, True):
+        mg.use_native_step = native
+        for graph in (False, True):
+            mg.use_cuda_graph = graph
+            mg.sampler_seed, mg.sampler_noise_fn = 9, None
+            outs[(native, graph)] = mg.generate(texts=["a"] * nb_, return_ids=True, **kw)
+        mg.use_cuda_graph = False
+        mg.sampler_noise_fn = util.torch_noise_fn(778)
+        outs[(native, "inject")] = mg.generate(texts=["a"] * nb_, return_ids=True, **kw)
+        mg.sampler_noise_fn = None
+    for key in (False, True, "inject"):
+        (ia, ta), (ib, tb) = outs[(False, key)], outs[(True, key)]
+        assert torch.equal(ta, tb), (key, int((ta != tb).sum()))
+        assert torch.equal(ia, ib), key
+    assert torch.equal(outs[(True, False)][1], outs[(True, True)][1])
+
+
+def test_ff_geglu_c_abi_vs_torch():
+    """mmg_ff_geglu: x += FeedForward(x) (LayerNorm -> GEGLU -> LayerNorm folded through the second product), optional constant added to
+    the tail rows first (the null-CFG cross-attention term)."""
+    from muse_maskgit_pytorch_b200 import ops
+    import torch.nn.functional as Fn
+    torch.manual_seed(5)
+    R, dim, F_ = 300, 128, 341
+    Fp = 384
+    bf = torch.bfloat16
+    x = torch.randn(R, dim) * 1.5
+    g0, g3 = 1 + 0.1 * torch.randn(dim), 1 + 0.1 * torch.randn(F_)
+    w1 = (torch.randn(2 * F_, dim) * dim ** -0.5).to(bf).float()
+    w2 = (torch.randn(dim, F_) * F_ ** -0.5)
+    add = torch.randn(dim) * 0.3
+    split = 200
+    # reference (fp32 math on the bf16-rounded operands the kernels see)
+    xr = x.clone(); xr[split:] += add
+    xn = Fn.layer_norm(xr, (dim,), g0, None, 1e-5).to(bf).float()
+    hcat = xn @ w1.t()
+    hh = (hcat[:, F_:] * Fn.gelu(hcat[:, :F_])).to(bf).float()
+    w2f = torch.zeros(dim, Fp); w2f[:, :F_] = w2 * g3[None]
+    w2f_b = w2f.to(bf)
+    want = xr + Fn.layer_norm(hh, (F_,), None, None, 1e-5) @ w2f_b.float()[:, :F_].t()
+    # packed operands (W1 rows interleaved in blocks of 32: [x(32) | gate(32)])
+    w1p = torch.zeros(2 * Fp, dim)
+    u = torch.arange(Fp); dst = u // 32 * 64 + u % 32; ok = u < F_
+    w1p[dst[ok]] = w1[:F_]; w1p[dst[ok] + 32] = w1[F_:]
+    xd = x.cuda()
+    ops.ff_geglu(xd, g0.cuda(), w1p.to(bf).cuda(), w2f_b.cuda(), w2f_b.float().sum(1).cuda(), F_,
+                 torch.empty(R, dim, dtype=bf, device="cuda"), torch.empty(R, Fp, dtype=bf, device="cuda"), torch.zeros(R, 2, device="cuda"),
+                 add=add.cuda(), add_from=split)
+    err = (xd.cpu() - want).abs().max().item()
+    assert err < 3e-2, err
+    assert rel_l2(xd, want) < 5e-3
