@@ -50,6 +50,44 @@ struct Epilogue {
   }
 
   // row: global output row (< M). col0: first accumulator column of this chunk (multiple of 64). nvalid: columns < N.
+  // QKV: which output a 64-column chunk belongs to (0 q, 1 k, 2 v), its head, and the l2-normalisation * scale of q / k in place
+  //   F.normalize(dim=-1, eps=1e-12) then * scale   (muse_maskgit_pytorch.py:151-153)
+  template <bool FAST>
+  __device__ __forceinline__ int qkv_chunk(int col0, float (&v)[64], int& h) const {
+    const int hc = col0 >> 6;
+    const int which = hc < p.nq_heads ? 0 : (hc < p.nq_heads + p.nk_heads ? 1 : 2);
+    h = which == 0 ? hc : (which == 1 ? hc - p.nq_heads : hc - p.nq_heads - p.nk_heads);
+    const float* sc = which == 0 ? p.q_scale : (which == 1 ? p.k_scale : nullptr);
+    if (sc) {
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};                    // four partial sums: 16-deep dependency chains instead of 64
+#pragma unroll
+      for (int i = 0; i < 64; ++i) s4[i & 3] = fmaf(v[i], v[i], s4[i & 3]);
+      const float ss = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      const float inv = FAST ? rsqrtf(fmaxf(ss, 1e-24f)) : 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = v[i] * inv * sc[i];
+    }
+    return which;
+  }
+  // the learned null key / value -> key row 0 of (b, h), written by the thread that owns token 0 (muse_maskgit_pytorch.py:145-149)
+  __device__ __forceinline__ void qkv_null_row(int which, int64_t b, int h) const {
+    const void* nsrc = which == 1 ? p.null_k : p.null_v;
+    if (!nsrc) return;
+    void* dst = which == 1 ? p.k_out : p.v_out;
+    const int64_t noff = ((b * p.heads + h) * (int64_t)p.kv_rows) * 64;
+    if (p.out_dtype == MMG_BF16) {
+      const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(nsrc) + h * 64);
+      uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(dst) + noff);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dp[i] = sp[i];
+    } else {
+      const float4* sp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(nsrc) + h * 64);
+      float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + noff);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dp[i] = sp[i];
+    }
+  }
+
   template <bool FAST>
   __device__ __forceinline__ void apply(int64_t row, int col0, float (&v)[64], int nvalid) {
     const bool bf = (p.out_dtype == MMG_BF16);
@@ -171,41 +209,14 @@ struct Epilogue {
         break;
       }
       case MMG_EPI_QKV: {
-        const int hc = col0 >> 6;
         const int64_t b = r_b, t = r_t;
-        void* dst; int h; int64_t off;
-        const float* sc = nullptr;
-        if (hc < p.nq_heads) { h = hc; dst = p.q_out; off = ((b * p.heads + h) * (int64_t)p.q_rows + t) * 64; sc = p.q_scale; }
-        else if (hc < p.nq_heads + p.nk_heads) { h = hc - p.nq_heads; dst = p.k_out; off = ((b * p.heads + h) * (int64_t)p.kv_rows + p.key_off + t) * 64; sc = p.k_scale; }
-        else { h = hc - p.nq_heads - p.nk_heads; dst = p.v_out; off = ((b * p.heads + h) * (int64_t)p.kv_rows + p.key_off + t) * 64; }
-        if (sc) {  // F.normalize(dim=-1, eps=1e-12) then * scale   (muse_maskgit_pytorch.py:151-153)
-          float s4[4] = {0.f, 0.f, 0.f, 0.f};                    // four partial sums: 16-deep dependency chains instead of 64
-#pragma unroll
-          for (int i = 0; i < 64; ++i) s4[i & 3] = fmaf(v[i], v[i], s4[i & 3]);
-          const float ss = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-          const float inv = FAST ? rsqrtf(fmaxf(ss, 1e-24f)) : 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] = v[i] * inv * sc[i];
-        }
+        int h;
+        const int which = qkv_chunk<FAST>(col0, v, h);
+        void* dst = which == 0 ? p.q_out : (which == 1 ? p.k_out : p.v_out);
+        const int64_t off = which == 0 ? ((b * p.heads + h) * (int64_t)p.q_rows + t) * 64 : ((b * p.heads + h) * (int64_t)p.kv_rows + p.key_off + t) * 64;
         if (bf) Vec64<bf16>::store(reinterpret_cast<bf16*>(dst) + off, v);
         else    Vec64<float>::store(reinterpret_cast<float*>(dst) + off, v);
-        if (t == 0 && hc >= p.nq_heads) {              // learned null key / value -> key row 0 (muse_maskgit_pytorch.py:145-149)
-          const void* nsrc = (hc < p.nq_heads + p.nk_heads) ? p.null_k : p.null_v;
-          if (nsrc) {
-            const int64_t noff = ((b * p.heads + h) * (int64_t)p.kv_rows) * 64;
-            if (bf) {
-              const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(nsrc) + h * 64);
-              uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(dst) + noff);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) dp[i] = sp[i];
-            } else {
-              const float4* sp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(nsrc) + h * 64);
-              float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + noff);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) dp[i] = sp[i];
-            }
-          }
-        }
+        if (t == 0 && which != 0) qkv_null_row(which, b, h);
         break;
       }
       case MMG_EPI_CONVT:

@@ -48,6 +48,20 @@ static int launch_tc_tstore(const TcGemmParams& p, cudaStream_t st) {
   return MMG_OK;
 }
 
+// QKV epilogue through per-warp tiles + TMA stores
+template <int BN>
+static int launch_tc_qkvt(const TcGemmParams& p, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES_RED); });
+  if (attr_err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(tc_gemm_qkvt<%d>): %s", BN, cudaGetErrorString(attr_err));
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  MMG_CUDA(launch_pdl(tc_gemm_kernel<BN, false, false, 4>, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES_RED, st, p));
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
 // LayerNorm-fused variant: clusters of two CTAs (column halves of the same rows), grid = 2 * min(#m-tiles, #SM / 2)
 template <int BN>
 static int launch_tc_lnf(const TcGemmParams& p, cudaStream_t st) {
@@ -132,10 +146,25 @@ static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_
   const bool plain_f32 = p.epi.kind == MMG_EPI_STORE && e.out_dtype == MMG_F32 && p.mode == 0 && !e.bias && e.act == 0 && (e.ldo % 4) == 0 && aligned16(e.out);
   static const int red_forced = [] { const char* ev = getenv("MMG_GEMM_RED"); return ev ? atoi(ev) : -1; }();
   static const int tstore_forced = [] { const char* ev = getenv("MMG_GEMM_TSTORE"); return ev ? atoi(ev) : -1; }();
-  const int epi_mode = (in_place && red_forced != 0) ? 2 : (plain_f32 && tstore_forced != 0 && bn == 256) ? 3 : 0;
-  const bool pair = use_pair(p, bn, epi_mode);
+  static const int qkvt_forced = [] { const char* ev = getenv("MMG_GEMM_QKVT"); return ev ? atoi(ev) : -1; }();
+  const bool qkv_tiles = p.epi.kind == MMG_EPI_QKV && e.out_dtype == MMG_BF16 && p.mode == 0 && e.tokens % 32 == 0 && p.M % 128 == 0 && (bn == 128 || bn == 256) &&
+                         (!e.nq_heads || aligned16(e.q_out)) && (!e.nk_heads || (aligned16(e.k_out) && aligned16(e.v_out))) && e.nk_heads == e.nv_heads;
+  const int epi_mode = (in_place && red_forced != 0) ? 2 : (plain_f32 && tstore_forced != 0 && bn == 256) ? 3 : (qkv_tiles && qkvt_forced != 0) ? 4 : 0;
+  const bool pair = use_pair(p, bn, epi_mode == 4 ? 0 : epi_mode);
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; uint64_t str[1] = {(uint64_t)ldw * 2}; uint32_t box[2] = {TC_BK, (uint32_t)(pair ? bn / 2 : bn)};
   int rc = make_tmap_bf16(&p.tma_b, w, 2, dims, str, box); if (rc) return rc;
+  if (epi_mode == 4) {
+    const uint64_t seqs = (uint64_t)(p.M / e.tokens) * (uint64_t)e.heads;
+    uint64_t str[1] = {128}; uint32_t box[2] = {64, 32};
+    if (e.nq_heads) { uint64_t d[2] = {64, seqs * (uint64_t)e.q_rows}; rc = make_tmap_bf16(&p.tma_qkv[0], e.q_out, 2, d, str, box); if (rc) return rc; }
+    if (e.nk_heads) {
+      uint64_t d[2] = {64, seqs * (uint64_t)e.kv_rows};
+      rc = make_tmap_bf16(&p.tma_qkv[1], e.k_out, 2, d, str, box); if (rc) return rc;
+      rc = make_tmap_bf16(&p.tma_qkv[2], e.v_out, 2, d, str, box); if (rc) return rc;
+    }
+    if (!pair) return bn == 256 ? launch_tc_qkvt<256>(p, st) : launch_tc_qkvt<128>(p, st);
+    return launch_tc_pair<256, 4>(p, st);
+  }
   if (epi_mode) {
     uint64_t od[2] = {(uint64_t)p.N, (uint64_t)p.M}; uint64_t os[1] = {(uint64_t)e.ldo * 4}; uint32_t ob[2] = {32, 32};
     rc = make_tmap_f32(&p.tma_out, e.out, 2, od, os, ob); if (rc) return rc;

@@ -27,7 +27,8 @@ constexpr int TC_MAX_TAPS = 16;
 struct alignas(64) TcGemmParams {
   CUtensorMap tma_a[4];
   CUtensorMap tma_b;
-  CUtensorMap tma_out;      // EPI_MODE 2: the fp32 output [M, N] in boxes of 32 rows x 32 columns (128 B), SWIZZLE_128B
+  CUtensorMap tma_out;      // EPI_MODE 2 / 3: the fp32 output [M, N] in boxes of 32 rows x 32 columns (128 B), SWIZZLE_128B
+  CUtensorMap tma_qkv[3];   // EPI_MODE 4: q / k / v as [rows, 64] bf16 matrices in boxes of 32 rows x 64 columns (128 B)
   int64_t M, N;
   int num_kb, num_m_tiles, num_n_tiles;
   int mode;                 // 0 dense, 1 conv (4-D A maps)
@@ -81,12 +82,15 @@ template <int BN> struct TcCfg {
 // in L2, and the L1 sees 8 conflict-free shared-memory stores per thread instead of 16 row-strided global accesses.
 // (Per-thread 128-byte bulk reductions were measured first: 52 -> 41 us on the wo GEMM, limited by the bulk-operation rate.)
 // EPI_MODE 3: plain fp32 outputs (no bias / activation; the logits GEMM) leave through the same tiles with a TMA store.
+// EPI_MODE 4: the QKV epilogue (bf16; tokens % 32 == 0 and M % 128 == 0, so a warp's 32 rows are 32 consecutive tokens of one
+// sequence and land on 32 consecutive rows of one head of q / k / v): head chunk -> tile -> one TMA store per warp and chunk.
 template <int BN, bool LNF = false, bool PAIR = false, int EPI_MODE = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   using namespace sm100;
   using Cfg = TcCfg<BN>;
   constexpr bool RED = EPI_MODE == 2 || EPI_MODE == 3, RED_ADD = EPI_MODE == 2;   // 3: same tiles, plain TMA store
+  constexpr bool QKVT = EPI_MODE == 4;
   static_assert(!(LNF && PAIR), "LayerNorm fusion and CTA pairs both claim the cluster");
   static_assert(!(LNF && EPI_MODE != 0), "the LayerNorm-fused kernel has no room for the epilogue tiles");
   constexpr int STAGES = PAIR ? Cfg::PAIR_STAGES : Cfg::STAGES;
@@ -280,7 +284,26 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
           released = true;
         }
         const int col0 = n_blk * BN + c * 64;
-        if (RED && col0 < p.N) {
+        if (QKVT && col0 < p.N) {
+          int h;
+          const int which = epi.template qkv_chunk<true>(col0, v, h);
+          const uint32_t wtile = smem_u32(smem + STAGES * STAGE_BYTES + 1024) + (uint32_t)(warp - 4) * 4096u;
+          const uint32_t rw = (uint32_t)(m_blk * TC_BM + quarter * 32), tok = (uint32_t)epi.p.tokens;
+          const uint32_t bq = rw / tok, t0 = rw - bq * tok;                       // warp-uniform: the 32 rows are tokens t0 .. t0+31 of sequence bq
+          const int64_t drow = which == 0 ? ((int64_t)bq * epi.p.heads + h) * epi.p.q_rows + t0
+                                          : ((int64_t)bq * epi.p.heads + h) * epi.p.kv_rows + epi.p.key_off + t0;
+          if (lane == 0) bulk_wait_read0();               // this warp's previous store has left the tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(wtile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) * 16)),
+                         "r"(pack_bf16(v[8 * j], v[8 * j + 1])), "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])),
+                         "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7])) : "memory");
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&p.tma_qkv[which], wtile, 0, (int)drow); bulk_commit(); }
+          if (which != 0 && t0 == 0 && lane == 0) epi.qkv_null_row(which, bq, h);
+        } else if (RED && col0 < p.N) {
           // rows past M hold garbage here and are clipped by the tensor map; the tile layout is the TMA 128-byte swizzle
           if (RED_ADD) epi.resid_term(col0, v);
           const uint32_t wtile = smem_u32(smem + STAGES * STAGE_BYTES + 1024) + (uint32_t)(warp - 4) * 4096u;
@@ -364,7 +387,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     }
   }
 
-  if (RED && warp >= 4 && lane == 0) bulk_wait0();   // every pushed tile has landed before the CTA (and its shared memory) goes away
+  if ((RED || QKVT) && warp >= 4 && lane == 0) bulk_wait0();   // every pushed tile has landed before the CTA (and its shared memory) goes away
   tc_fence_before();
   __syncthreads();
   if (LNF || PAIR) cluster_sync_all();          // no CTA may exit while its peer can still write its shared memory / read its operands

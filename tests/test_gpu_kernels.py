@@ -571,3 +571,38 @@ def test_linear_wide_tiles_tma_epilogues():
     ops().linear(dev(a, bf), dev(w, bf), xd, epilogue=ops().EPI_RESIDUAL, resid=xd)
     ok, msg = close(xd, x + 2 * (a @ w.t()), 5e-4)
     assert ok, msg
+
+
+@pytest.mark.parametrize("b,q_only", [(16, False), (32, False), (32, True)], ids=["bn128", "bn256", "q_only"])
+def test_linear_qkv_epilogue_tma_tiles(b, q_only):
+    """The QKV epilogue at shapes where it leaves through per-warp tiles + TMA stores (tokens % 32 == 0, M % 128 == 0, 128- or
+    256-column tiles): same contract as test_linear_qkv_epilogue, incl. the null key/value row and untouched padding rows."""
+    bf = torch.bfloat16
+    n, heads, dim = 256, 8, 128
+    inner = heads * 64
+    nsec = 1 if q_only else 3
+    x = rnd("xq", (b * n, dim), bf)
+    w = rnd("wq3", (nsec * inner, dim), bf, std=dim ** -0.5)
+    qs, ks = 1 + 0.1 * rnd("qs", (64,)), 1 + 0.1 * rnd("ks", (64,))
+    nk, nv = rnd("nk8", (heads, 64), bf), rnd("nv8", (heads, 64), bf)
+    q = torch.zeros((b * heads + 3, n, 64), device="cuda", dtype=bf)          # 3 guard blocks past the tensor the epilogue is told about
+    k = torch.zeros((b * heads, n + 8, 64), device="cuda", dtype=bf)
+    v = torch.zeros_like(k)
+    qsd, ksd, nkd, nvd = dev(qs), dev(ks), dev(nk, bf), dev(nv, bf)
+    if q_only:
+        e = ops().qkv_epilogue(bf, heads, n, q=q[:b * heads], q_scale=qsd)
+    else:
+        e = ops().qkv_epilogue(bf, heads, n, q=q[:b * heads], k=k, v=v, q_scale=qsd, k_scale=ksd, key_off=1, null_k=nkd, null_v=nvd)
+    ops().linear(dev(x, bf), dev(w, bf), None, epilogue=ops().EPI_QKV, epi=e)
+    y = (x @ w.t()).view(b, n, nsec, heads, 64).permute(2, 0, 3, 1, 4)
+    ok, msg = close(q[:b * heads].view(b, heads, n, 64), F.normalize(y[0], dim=-1) * qs, 2e-2, 1e-2)
+    assert ok, "q: " + msg
+    assert float(q[b * heads:].abs().max()) == 0.
+    if not q_only:
+        kk, vv = k.view(b, heads, n + 8, 64), v.view(b, heads, n + 8, 64)
+        ok, msg = close(kk[:, :, 1:n + 1], F.normalize(y[1], dim=-1) * ks, 2e-2, 1e-2)
+        assert ok, "k: " + msg
+        ok, msg = close(vv[:, :, 1:n + 1], y[2], 2e-2, 1e-2)
+        assert ok, "v: " + msg
+        assert torch.equal(kk[:, :, 0].float().cpu(), nk.expand(b, -1, -1)) and torch.equal(vv[:, :, 0].float().cpu(), nv.expand(b, -1, -1))
+        assert float(kk[:, :, n + 1:].abs().max()) == 0. and float(vv[:, :, n + 1:].abs().max()) == 0.
