@@ -57,3 +57,12 @@ def test_state_dict_keys_match_reference_tables():
     assert "quantizer.mask" in vae.state_dict()
     critic = M.TokenCritic(num_tokens=1024, dim=128, seq_len=16, depth=1, heads=2, t5_name="synth-96")
     assert critic.state_dict()["to_logits.weight"].shape == (1, 128) and critic.mask_id is None
+
+
+def test_decode_step_workspace_query_is_host_only():
+    """mmg_decode_step_workspace_bytes is pure host arithmetic: callable without a GPU, grows with the logits buffer."""
+    from muse_maskgit_pytorch_b200 import _lib
+    f = _lib.lib().mmg_decode_step_workspace_bytes
+    c3 = f(64, 2, 256, 512, 8, 1408, 65536, 256)
+    assert c3 >= 64 * 256 * 65536 * 4 and c3 % 256 == 0
+    assert f(8, 2, 256, 512, 8, 1408, 65536, 256) < c3 and f(0, 2, 256, 512, 8, 1408, 65536, 256) == 0

@@ -140,3 +140,23 @@ def test_philox_known_answer():
     assert int(round(float(u[0]) * (1 << 24))) == 0x6627e8d5 >> 8
     a, b = philox.uniform(5, 1, 2, 64), philox.uniform(5, 1, 3, 64)
     assert not np.array_equal(a, b) and a.min() >= 0 and a.max() < 1
+
+
+def test_aten_uniform_model_known_answers():
+    """oracle/philox.aten_uniform restates ATen's CUDA uniform_ stream (pinned against torch.cuda itself on the GPU box,
+    tests/test_gpu_aten_rng.py).  Offline regression: the first values of `torch.manual_seed(0); torch.rand(3, device="cuda")`
+    and the launch geometry / generator-offset bookkeeping for the C3 noise tensor on a 148-SM device."""
+    from oracle import philox
+    u = philox.aten_uniform(0, 0, 3, philox.aten_stride(3, 148, 2048))
+    assert [f"{x:.4f}" for x in u] == ["0.3990", "0.5167", "0.0249"]
+    numel = 64 * 256 * 65536
+    stride = philox.aten_stride(numel, 148, 2048)
+    assert stride == 148 * 8 * 256 and philox.aten_offset_increment(numel, stride) == ((numel - 1) // (stride * 4) + 1) * 4 == 3544
+    # element li = t + stride * (4 j + ii) is word ii of Philox(counter = offset / 4 + j, subsequence = t): spot-check the indexing
+    li = np.array([5, stride + 5, 4 * stride + 5], dtype=np.uint64)
+    a = philox.aten_uniform(7, 8, numel, stride, index=li)
+    w = philox.philox4(np.array([2, 2, 3], dtype=np.uint64), 0, np.array([5, 5, 5], dtype=np.uint64), 0, 7, 0)
+    want = [float(np.float32(w[0][0]) * np.float32(2.0 ** -32) + np.float32(2.0 ** -33)),
+            float(np.float32(w[1][1]) * np.float32(2.0 ** -32) + np.float32(2.0 ** -33)),
+            float(np.float32(w[0][2]) * np.float32(2.0 ** -32) + np.float32(2.0 ** -33))]
+    assert [float(x) for x in a] == want
