@@ -2,11 +2,13 @@
 //
 //   warp 0      : TMA producer  (one elected lane) — A tile 128x64 and W tile BNx64 per k-block, SWIZZLE_128B
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane) — 4 x tcgen05.mma (K=16) per k-block, M=128, N=BN
-//   warps 4..11 : epilogue — tcgen05.ld (32 lanes x 32 cols) -> registers -> fused Epilogue -> global; two warps share a TMEM
-//                 lane quarter and take alternate 64-column chunks.  setmaxnreg moves registers from warpgroup 0 (40/thread)
-//                 to the epilogue warpgroups (232/thread) so a residual chunk can be prefetched while the MMA is in flight.
-//   persistent grid (<= #SM CTAs), static tile schedule, STAGES-deep smem ring, 2 accumulator stages in TMEM so the
-//   epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 4..11 : epilogue — tcgen05.ld (32 lanes x 32 cols) -> registers -> fused Epilogue -> global (directly, or through a per-warp
+//                 shared-memory tile and a TMA store / TMA reduction, see EPI_MODE below); two warps share a TMEM lane quarter and
+//                 take alternate 64-column chunks.  setmaxnreg moves registers from warpgroup 0 (40/thread) to the epilogue
+//                 warpgroups (232/thread).
+//   persistent grid (<= #SM CTAs), static tile schedule (M- or N-fastest), STAGES-deep smem ring, 2 accumulator stages in TMEM so
+//   the epilogue of tile i overlaps the main loop of tile i+1.  Variants: LNF (LayerNorm of the output row through a 2-CTA
+//   cluster), PAIR (tcgen05 cta_group::2: one 256 x BN tile per CTA pair).
 //
 // A is either a dense [M,K] matrix (2-D tensor map) or an NHWC activation addressed as an implicit-GEMM
 // convolution: the k-block (tap, channel-chunk) is fetched with a 4-D tensor map at shifted (x+dx, y+dy)
