@@ -573,8 +573,8 @@ class MaskGit(nn.Module):
                 out_images, out_ids = body(te_s, ci_s)
             # the entry keeps alive everything the captured kernels point at (packed weights, workspaces)
             entry = (graph, te_s, ci_s, out_images, out_ids, pack_ids(),
-                     (tr._pack, self.vae._pack, self.cond_vae._pack, dict(tr._ws),
-                      None if critic_net is None else (critic_net._pack, dict(critic_net._ws)),
+                     (tr._pack, self.vae._pack, self.cond_vae._pack, dict(getattr(tr, "_ws", {})),
+                      None if critic_net is None else (critic_net._pack, dict(getattr(critic_net, "_ws", {}))),
                       self.token_critic._head_cache if isinstance(self.token_critic, SelfCritic) else None))
             if len(self._graphs) >= 4:
                 self._graphs.pop(next(iter(self._graphs)))
