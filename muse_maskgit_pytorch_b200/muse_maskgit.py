@@ -87,15 +87,28 @@ class Transformer(nn.Module):
         self.self_cond_to_init_embed = _ff_params(dim)
         self.precision = precision or "bf16"
         self._pack = None
+        # nn.Module.load_state_dict on a PARENT never calls a child's load_state_dict override, but it does run the child's
+        # post hooks: the packed weights are dropped whichever module the load was started from
+        self.register_load_state_dict_post_hook(lambda m, _inc: m._invalidate())
 
     # ----- packing ------------------------------------------------------------------------------------------------
-    def _apply(self, fn, *a, **k):
+    def _invalidate(self):
         self._pack = None
+        self.__dict__.pop("_ws", None)
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
         return super()._apply(fn, *a, **k)
 
-    def load_state_dict(self, *a, **k):
-        self._pack = None
-        return super().load_state_dict(*a, **k)
+    def _weights_sig(self):
+        """(storage, version) of every parameter: catches in-place edits (`p.data.copy_`, optimizer steps) between calls."""
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _check_weights(self):
+        sig = self._weights_sig()
+        if self._pack is not None and self._pack.get("sig") != sig:
+            self._invalidate()
+        return sig
 
     def _adt(self):
         return torch.bfloat16 if self.precision == "bf16" else torch.float32
@@ -153,6 +166,7 @@ class Transformer(nn.Module):
         P["whead"] = f32(self.to_logits.weight).reshape(-1) if self.dim_out == 1 else None     # TokenCritic head, applied in mmg_critic_score
         P["wproj"] = wa(self.text_embed_proj.weight) if isinstance(self.text_embed_proj, nn.Linear) else None
         P["sc"] = ff_pack(self.self_cond_to_init_embed) if self.self_cond else None
+        P["sig"] = self._weights_sig()
         self._pack = P
         return P
 
@@ -211,7 +225,7 @@ class Transformer(nn.Module):
         adt, tb = P["adt"], self.transformer_blocks
         heads, dim, inner = tb.heads, self.dim, tb.heads * 64
         R = nb * b * n
-        Fp = max(l["ff"]["Fp"] for l in P["layers"])
+        Fp = max([l["ff"]["Fp"] for l in P["layers"]] + ([P["sc"]["Fp"]] if P["sc"] is not None else []))
         tk_alloc = _round_up(n + 1, 8)
         ws = dict(key=key,
                   x=torch.empty((R, dim), device=dev, dtype=torch.float32),
@@ -417,19 +431,17 @@ class SelfCritic(nn.Module):
         self.net = net
         self.to_pred = nn.Linear(net.dim, 1)
         self._head_cache = None
+        self.register_load_state_dict_post_hook(lambda m, _inc: setattr(m, "_head_cache", None))
 
     def _apply(self, fn, *a, **k):
         self._head_cache = None
         return super()._apply(fn, *a, **k)
 
-    def load_state_dict(self, *a, **k):
-        self._head_cache = None
-        return super().load_state_dict(*a, **k)
-
     def _head(self):
-        if self._head_cache is None:          # one host read of the bias per weight load, not per generate()
-            self._head_cache = (self.to_pred.weight.detach().float().reshape(-1).contiguous(), float(self.to_pred.bias.detach().float().item()))
-        return self._head_cache
+        sig = (self.to_pred.weight._version, self.to_pred.bias._version, self.to_pred.weight.data_ptr())
+        if self._head_cache is None or self._head_cache[2] != sig:      # one host read of the bias per weight load, not per generate()
+            self._head_cache = (self.to_pred.weight.detach().float().reshape(-1).contiguous(), float(self.to_pred.bias.detach().float().item()), sig)
+        return self._head_cache[:2]
 
     @torch.no_grad()
     def forward_with_cond_scale(self, x, *args, **kwargs):
@@ -493,6 +505,11 @@ class MaskGit(nn.Module):
         self.use_native_step = False        # True: one mmg_decode_step call per step (the same launch sequence issued from C++)
         self._graphs = {}
         self.row_offset = 0                 # global index of this shard's first sequence (multi-GPU batch sharding)
+        self.register_load_state_dict_post_hook(lambda m, _inc: m._graphs.clear())
+
+    def _apply(self, fn, *a, **k):
+        self.__dict__.get("_graphs", {}).clear()
+        return super()._apply(fn, *a, **k)
 
     def save(self, path):
         torch.save(self.state_dict(), path)
@@ -531,7 +548,14 @@ class MaskGit(nn.Module):
         fmap_size = fmap_size if fmap_size is not None else self.vae.get_encoded_fmap_size(self.image_size)
         device = next(self.parameters()).device
         b = len(texts)
+        for net in (tr, self.vae, self.cond_vae, self.token_critic if isinstance(self.token_critic, Transformer) else None):
+            if net is not None:
+                net._check_weights()          # in-place parameter edits since the last call drop the packed copies (and the graphs below)
         text_embeds = tr.encode_text(texts).to(device, non_blocking=True)
+        if self.use_cuda_graph and text_embeds.shape[1] % 32:
+            # T5 pads to the longest prompt of the batch: bucket the length (multiples of 32) so that prompt lengths share captured
+            # graphs; all-zero rows are padding to the reference too (masked keys, muse_maskgit_pytorch.py:304)
+            text_embeds = torch.nn.functional.pad(text_embeds, (0, 0, 0, 32 - text_embeds.shape[1] % 32))
         if self.resize_image_for_cond_image:
             assert cond_images is not None, "conditioning image must be passed in to generate for super res maskgit"
             cond_images = cond_images.to(device, torch.float32)
@@ -544,7 +568,7 @@ class MaskGit(nn.Module):
         aten = None
         if self.sampler_rng == "aten" and self.sampler_noise_fn is None:
             aten = self._aten_plan(device, b, fmap_size ** 2, tr.num_tokens, timesteps, use_critic)
-        else:
+        elif self.sampler_noise_fn is None:      # (injected noise: the host generator is the caller's stream — nothing is drawn from it here)
             seed = self.sampler_seed if self.sampler_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
             self._seed_dev.fill_(seed)
         body = partial(self._generate_body, fmap_size=fmap_size, temperature=temperature, topk_filter_thres=topk_filter_thres,
@@ -557,7 +581,8 @@ class MaskGit(nn.Module):
         # ---- whole-call CUDA graph: 18 decode steps + VAE decode replayed as one launch (no per-kernel host work) ----
         key = (b, tuple(text_embeds.shape), text_embeds.dtype, None if cond_images is None else tuple(cond_images.shape), fmap_size,
                float(temperature), float(topk_filter_thres), int(timesteps), float(cond_scale), int(self.row_offset), tr.precision, self.vae.precision,
-               use_critic, float(critic_noise_scale), bool(can_remask_prev_masked), None if aten is None else aten["key"], bool(self.use_native_step))
+               use_critic, float(critic_noise_scale), bool(can_remask_prev_masked), None if aten is None else aten["key"], bool(self.use_native_step),
+               id(self.noise_schedule), os.environ.get("MMG_FUSE_LN", "0"))
         pack_ids = lambda: (id(tr._pack), id(self.vae._pack), id(self.cond_vae._pack), id(critic_net._pack) if critic_net is not None else 0,
                             id(self.token_critic._head_cache) if isinstance(self.token_critic, SelfCritic) else 0)
         entry = self._graphs.get(key)
@@ -577,8 +602,9 @@ class MaskGit(nn.Module):
                       None if critic_net is None else (critic_net._pack, dict(getattr(critic_net, "_ws", {}))),
                       self.token_critic._head_cache if isinstance(self.token_critic, SelfCritic) else None))
             if len(self._graphs) >= 4:
-                self._graphs.pop(next(iter(self._graphs)))
-            self._graphs[key] = entry
+                self._graphs.pop(next(iter(self._graphs)))       # least recently used (hits are moved to the end below)
+        self._graphs.pop(key, None)
+        self._graphs[key] = entry
         graph, te_s, ci_s, out_images, out_ids = entry[:5]
         te_s.copy_(text_embeds, non_blocking=True)
         if ci_s is not None:

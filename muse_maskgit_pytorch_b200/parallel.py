@@ -37,14 +37,32 @@ def gather_batch(local, total, group=None):
 
 def generate_sharded(maskgit, texts, text_embeds=None, cond_images=None, group=None, **generate_kwargs):
     """maskgit.generate over this rank's slice of `texts` (+ optional pre-computed `text_embeds` [B, L, D] and
-    `cond_images` [B, ...], indexed by global row), then one all-gather.  Returns the full batch on every rank."""
+    `cond_images` [B, ...], indexed by global row), then one all-gather.  Returns the full batch on every rank.
+
+    The sampler noise is keyed on the global sequence index, so the token ids do not depend on the number of ranks:
+    "mmg" mode uses ONE seed for all ranks (rank 0's `sampler_seed`, or its draw from torch's generator, broadcast);
+    "aten" mode is told the size of the whole batch the reference would have drawn noise for (`global_batch`)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     total = len(texts)
     lo, hi = shard_bounds(total, rank, world)
-    maskgit.row_offset = lo
-    if text_embeds is not None:
-        shard = text_embeds[lo:hi]
-        maskgit.transformer.encode_text = lambda t: shard
-    local = maskgit.generate(texts[lo:hi], cond_images=None if cond_images is None else cond_images[lo:hi], **generate_kwargs)
+    tr = maskgit.transformer
+    saved = (tr.encode_text, maskgit.row_offset, maskgit.global_batch, maskgit.sampler_seed)
+    try:
+        seed = maskgit.sampler_seed if maskgit.sampler_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        if world > 1:
+            box = [seed]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            seed = box[0]
+        maskgit.sampler_seed, maskgit.row_offset, maskgit.global_batch = seed, lo, total
+        if text_embeds is not None:
+            shard = text_embeds[lo:hi]
+            tr.encode_text = lambda t: shard
+        if hi > lo:
+            local = maskgit.generate(texts[lo:hi], cond_images=None if cond_images is None else cond_images[lo:hi], **generate_kwargs)
+        else:       # more ranks than sequences: this rank contributes an empty shard of the right shape / dtype / device
+            size = maskgit.image_size
+            local = torch.empty((0, maskgit.vae.channels, size, size), dtype=torch.float32, device=next(maskgit.parameters()).device)
+    finally:
+        tr.encode_text, maskgit.row_offset, maskgit.global_batch, maskgit.sampler_seed = saved
     return gather_batch(local, total, group)

@@ -111,6 +111,22 @@ class VQGanVAE(nn.Module):
         self.discr, self._vgg = None, None
         self.precision = precision or "bf16"
         self._pack = None
+        # both hooks also fire when a PARENT module (MaskGit, Muse) loads a checkpoint: checkpoints written by the reference carry
+        # discriminator / VGG tensors (vqgan_vae.py:344-348, dropped by copy_for_eval :394-403) that are not part of inference
+        self._register_load_state_dict_pre_hook(self._drop_training_only_keys)
+        self.register_load_state_dict_post_hook(lambda m, _inc: setattr(m, "_pack", None))
+
+    @staticmethod
+    def _drop_training_only_keys(state_dict, prefix, *_):
+        for k in [k for k in state_dict if k.startswith((prefix + "discr.", prefix + "_vgg."))]:
+            del state_dict[k]
+
+    def _weights_sig(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _check_weights(self):
+        if self._pack is not None and self._pack.get("sig") != self._weights_sig():
+            self._pack = None
 
     # ----- reference surface ------------------------------------------------------------------------------------
     @property
@@ -133,12 +149,6 @@ class VQGanVAE(nn.Module):
         c = copy.deepcopy(self)
         c._pack = None
         return c.eval()
-
-    def load_state_dict(self, state_dict, strict=True, **kw):
-        # checkpoints written by the reference carry discriminator / VGG tensors; they are not part of inference
-        sd = {k: v for k, v in state_dict.items() if not k.startswith(("discr.", "_vgg."))}
-        self._pack = None
-        return super().load_state_dict(sd, strict=strict, **kw)
 
     def save(self, path):
         torch.save(self.state_dict(), path)
@@ -218,6 +228,7 @@ class VQGanVAE(nn.Module):
             P["codebook"] = f32(q.embed)
             P["codebook_a"] = P["codebook"].to(adt).contiguous()
             P["code_norms"] = (P["codebook_a"].float() ** 2).sum(-1).contiguous()
+        P["sig"] = self._weights_sig()
         self._pack = P
         return P
 

@@ -196,4 +196,58 @@ save("gen_selfcritic_small", images=images, ids=ids, w_pred=wp, b_pred=bp)
 mg_rm = MaskGit(image_size=16, transformer=tr, vae=vae_s, no_mask_token_prob=0.1).eval()
 images, ids = run_generate(mg_rm, 8, 782, can_remask_prev_masked=True)
 save("gen_remask_prev_small", images=images, ids=ids)
+
+# ------------------------------------------------------------------ G10: Muse cascade (muse_maskgit_pytorch.py:745-791) on the G4 / G5 models
+from muse_maskgit_pytorch import Muse                               # noqa: E402
+
+tr.encode_text = lambda texts: te[:2]
+tr2.encode_text = lambda texts: te[:2]
+muse = Muse(base=mg, superres=mg2)
+torch.manual_seed(783)
+calls = []
+orig = vae_s.decode_from_ids           # base.vae and superres.vae are both eval copies of vae_s: wrap each
+wrapped = []
+for m_ in (mg, mg2):
+    o_ = m_.vae.decode_from_ids
+    wrapped.append((m_.vae, o_))
+    m_.vae.decode_from_ids = lambda ids_, _o=o_: (calls.append(ids_.clone()), _o(ids_))[1]
+sup, low = muse(["a"] * 2, timesteps=6, superres_timesteps=8, return_lowres=True, return_pil_images=False)
+for v_, o_ in wrapped:
+    v_.decode_from_ids = o_
+assert len(calls) == 2
+save("muse_small", lowres=low, superres=sup, base_ids=calls[0], superres_ids=calls[1])
+
+# ------------------------------------------------------------------ G11: checkpoints WRITTEN BY THE REFERENCE (save(): muse_maskgit_pytorch.py:482-489,
+# vqgan_vae.py:405-420), default-initialised modules; the cond_vae of the super-res model is a full VQGanVAE (with its discriminator,
+# whose tensors the reference saves under cond_vae.discr.*), and the cascade output those weights produce
+seed_t5("synth-64", 64)
+torch.manual_seed(900)
+vae_ck = VQGanVAE(dim=16, layers=2, codebook_size=256)
+vae_ck2 = VQGanVAE(dim=16, layers=2, codebook_size=256)
+tr_b = MaskGitTransformer(num_tokens=256, dim=64, seq_len=16, depth=1, dim_head=64, heads=1, t5_name="synth-64", flash=False)
+tr_s = MaskGitTransformer(num_tokens=256, dim=64, seq_len=64, depth=1, dim_head=64, heads=1, t5_name="synth-64", flash=False)
+base_ck = MaskGit(image_size=16, transformer=tr_b, vae=vae_ck).eval()
+sr_ck = MaskGit(image_size=32, transformer=tr_s, vae=vae_ck, cond_vae=vae_ck2, cond_image_size=16).eval()
+vae_ck.eval().save(os.path.join(HERE, "ckpt_vae.pt"))
+base_ck.save(os.path.join(HERE, "ckpt_base.pt"))
+sr_ck.save(os.path.join(HERE, "ckpt_superres.pt"))
+sd_sr = torch.load(os.path.join(HERE, "ckpt_superres.pt"))
+assert any(k.startswith("cond_vae.discr.") for k in sd_sr) and any(k.startswith("discr.") for k in torch.load(os.path.join(HERE, "ckpt_vae.pt")))
+te64 = text_embeds("g11.te", 2, 8, 64, 31)
+tr_b.encode_text = lambda texts: te64
+tr_s.encode_text = lambda texts: te64
+muse_ck = Muse(base=base_ck, superres=sr_ck)
+torch.manual_seed(901)
+calls = []
+wrapped = []
+for m_ in (base_ck, sr_ck):
+    o_ = m_.vae.decode_from_ids
+    wrapped.append((m_.vae, o_))
+    m_.vae.decode_from_ids = lambda ids_, _o=o_: (calls.append(ids_.clone()), _o(ids_))[1]
+sup, low = muse_ck(["a"] * 2, timesteps=4, superres_timesteps=4, return_lowres=True, return_pil_images=False)
+for v_, o_ in wrapped:
+    v_.decode_from_ids = o_
+img = torch.from_numpy(synth.uniform("g11.img", (2, 3, 16, 16), 31))
+_, vids, _ = vae_ck.encode(img)
+save("ckpt_muse", lowres=low, superres=sup, base_ids=calls[0], superres_ids=calls[1], vae_ids=vids.long(), vae_recon=vae_ck.decode_from_ids(vids))
 print("done")

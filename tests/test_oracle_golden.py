@@ -160,3 +160,45 @@ def test_aten_uniform_model_known_answers():
             float(np.float32(w[1][1]) * np.float32(2.0 ** -32) + np.float32(2.0 ** -33)),
             float(np.float32(w[0][2]) * np.float32(2.0 ** -32) + np.float32(2.0 ** -33))]
     assert [float(x) for x in a] == want
+
+
+def _noise_stream(seed):
+    """One torch CPU stream across BOTH generate() calls of the cascade (the reference seeds once, muse_maskgit_pytorch.py:758-791)."""
+    torch.manual_seed(seed)
+    return lambda step, shape: torch.zeros(shape).uniform_(0, 1)
+
+
+def test_muse_cascade_small():
+    """Muse.forward = base generate -> super-res generate conditioned on the low-res images (golden G10, unmodified reference)."""
+    g = util.golden("muse_small")
+    vsd = util.vae_sd(16, 2, 1024, seed=12)
+    te = util.text_embeds("g4.te", 3, 8, 128, 14)[:2]
+    noise = _noise_stream(783)
+    low, base_ids = O.generate(util.transformer_sd(1024, 128, 16, 2, 2, seed=13, text_dim=128), CFG, vsd, 10, te, 4, noise, timesteps=6)
+    assert torch.equal(base_ids.view(2, 4, 4), g["base_ids"])
+    assert torch.allclose(low, g["lowres"], atol=1e-5)
+    sup, sr_ids = O.generate(util.transformer_sd(1024, 128, 64, 2, 2, seed=15, text_dim=128), CFG, vsd, 10, te, 8, noise, cond_images=low, timesteps=8)
+    assert torch.equal(sr_ids.view(2, 8, 8), g["superres_ids"])
+    assert torch.allclose(sup, g["superres"], atol=1e-5)
+
+
+def test_reference_written_checkpoints():
+    """Checkpoints saved by the reference's own save() (G11): the oracle on those weights reproduces the reference's cascade, and the
+    files carry the training-only tensors (discr.*) the drop-in has to skip."""
+    import os
+    g = util.golden("ckpt_muse")
+    load = lambda n: torch.load(os.path.join(util.GOLDEN, n), map_location="cpu")
+    base, sr, vae = load("ckpt_base.pt"), load("ckpt_superres.pt"), load("ckpt_vae.pt")
+    assert any(k.startswith("discr.") for k in vae) and any(k.startswith("cond_vae.discr.") for k in sr)
+    sub = lambda sd, pre: {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+    cfg = dict(heads=1, depth=1)
+    te = util.text_embeds("g11.te", 2, 8, 64, 31)
+    img = torch.from_numpy(synth.uniform("g11.img", (2, 3, 16, 16), 31))
+    _, vids = O.vae_encode(vae, img)
+    assert torch.equal(vids, g["vae_ids"])
+    assert torch.allclose(O.vae_decode_from_ids(vae, vids, 8), g["vae_recon"], atol=1e-5)
+    noise = _noise_stream(901)
+    low, base_ids = O.generate(sub(base, "transformer."), cfg, sub(base, "vae."), 8, te, 4, noise, timesteps=4)
+    assert torch.equal(base_ids.view(2, 4, 4), g["base_ids"]) and torch.allclose(low, g["lowres"], atol=1e-5)
+    sup, sr_ids = O.generate(sub(sr, "transformer."), cfg, sub(sr, "vae."), 8, te, 8, noise, cond_images=low, sd_cond_vae=sub(sr, "cond_vae."), timesteps=4)
+    assert torch.equal(sr_ids.view(2, 8, 8), g["superres_ids"]) and torch.allclose(sup, g["superres"], atol=1e-5)

@@ -13,9 +13,15 @@ class StubMaskGit:
     """generate() returns images that encode (global row, text embedding sum) so order and offsets are checkable."""
     class _T:
         encode_text = None
-    def __init__(self):
-        self.transformer, self.row_offset = self._T(), 0
+    class _V:
+        channels = 3
+    def __init__(self, seed=None):
+        self.transformer, self.row_offset, self.global_batch, self.sampler_seed = self._T(), 0, None, seed
+        self.image_size, self.vae, self.seen = 4, self._V(), []
+    def parameters(self):
+        yield torch.zeros(1)
     def generate(self, texts, cond_images=None, **kw):
+        self.seen.append((self.sampler_seed, self.global_batch, self.row_offset))
         te = self.transformer.encode_text(texts)
         rows = torch.arange(self.row_offset, self.row_offset + len(texts), dtype=torch.float32)
         img = rows[:, None, None, None] * torch.ones((len(texts), 3, 4, 4)) + te.sum(dim=(1, 2))[:, None, None, None] * 1000
@@ -29,7 +35,14 @@ def _worker(rank, world, port, total, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     te = torch.arange(total * 6, dtype=torch.float32).view(total, 2, 3)
     cond = torch.arange(total, dtype=torch.float32).view(total, 1, 1, 1).expand(total, 3, 2, 2).contiguous()
-    out = parallel.generate_sharded(StubMaskGit(), ["t"] * total, text_embeds=te, cond_images=cond, timesteps=3)
+    mg = StubMaskGit(seed=None if rank else 4242)       # rank 0's seed must reach every rank
+    sentinel = mg.transformer.encode_text
+    out = parallel.generate_sharded(mg, ["t"] * total, text_embeds=te, cond_images=cond, timesteps=3)
+    # the call leaves the model as it found it (encode_text / row_offset / global_batch / seed were left overwritten)
+    assert mg.transformer.encode_text is sentinel and mg.row_offset == 0 and mg.global_batch is None
+    assert mg.sampler_seed == (None if rank else 4242)
+    lo, hi = parallel.shard_bounds(total, rank, world)
+    assert mg.seen == ([(4242, total, lo)] if hi > lo else []), mg.seen
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -55,7 +68,7 @@ def test_shard_bounds():
 
 
 def test_two_ranks_equal_single_rank_even_and_uneven():
-    for total, port in ((8, 29611), (7, 29612)):
+    for total, port in ((8, 29611), (7, 29612), (1, 29613)):       # even, uneven, and an empty shard on rank 1
         outs = _run(total, port)
         te = torch.arange(total * 6, dtype=torch.float32).view(total, 2, 3)
         cond = torch.arange(total, dtype=torch.float32).view(total, 1, 1, 1).expand(total, 3, 2, 2).contiguous()
