@@ -266,6 +266,9 @@ typedef struct {
   const void* x; int32_t dtype;            /* [T, D] token-major fmap                                              */
   const float* w_in; const float* b_in;    /* [bits, D], [bits]; NULL -> identity (D == bits)                     */
   int64_t* ids; int64_t T; int32_t D, bits;
+  const void* w_split;                     /* optional, bf16 tokens: [64, D] bf16, rows [hi(bits) | mid(bits) | lo(bits) | 0...] = the 3-way bf16
+                                              split of w_in (hi + mid + lo == w_in in fp32; 3 * bits <= 64, D % 64 == 0): the projection then
+                                              runs on the tcgen05 path (mmg_linear + MMG_EPI_LFQ_IDS), one TMA stream over the tokens      */
 } mmg_vq_lfq_encode_args;
 int mmg_vq_lfq_encode(const mmg_vq_lfq_encode_args* a, void* stream);
 

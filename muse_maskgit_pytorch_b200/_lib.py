@@ -112,7 +112,7 @@ class DecodeStepArgs(C.Structure):
 
 
 class LfqEncodeArgs(C.Structure):
-    _fields_ = [("x", vp), ("dtype", i32), ("w_in", vp), ("b_in", vp), ("ids", vp), ("T", i64), ("D", i32), ("bits", i32)]
+    _fields_ = [("x", vp), ("dtype", i32), ("w_in", vp), ("b_in", vp), ("ids", vp), ("T", i64), ("D", i32), ("bits", i32), ("w_split", vp)]
 
 
 class L2ArgminArgs(C.Structure):

@@ -5,12 +5,71 @@
 namespace mmg {
 
 // LFQ encode: the nearest code of the implicit {+-1}^bits codebook is the sign pattern of the projected token.
-// One warp per token: 128-bit coalesced loads of the token's D channels, `bits` running dot products against the
-// projection rows held in shared memory, warp-shuffle reduction, then bit-pack (MSB first; x == 0 -> bit 0).
+// CUDA-core path (fp32 "parity" precision; bf16 inputs normally take the tcgen05 route below).  The projection [bits, D] sits in
+// shared memory; a warp owns LFQ_TOK tokens at a time and a lane 4 channels of each (one 128-bit / 64-bit load per token), so one
+// 128-bit shared-memory read of a weight quad feeds 4 x LFQ_TOK FMAs (0.06 shared reads per FMA instead of 1) and the token
+// stream is fully coalesced.  Warp-shuffle reduction, then bit-pack (MSB first; x == 0 -> bit 0).
+constexpr int LFQ_TOK = 4;
+template <typename T> __device__ __forceinline__ float4 lfq_load4(const T* p);
+template <> __device__ __forceinline__ float4 lfq_load4<float>(const float* p) {
+  float4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return v;
+}
+template <> __device__ __forceinline__ float4 lfq_load4<bf16>(const bf16* p) {
+  uint32_t a, b; asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+  return make_float4(__uint_as_float(a << 16), __uint_as_float(a & 0xffff0000u), __uint_as_float(b << 16), __uint_as_float(b & 0xffff0000u));
+}
+
 template <typename T, int BITS_MAX>
 __global__ void __launch_bounds__(256)
 lfq_encode_kernel(const T* __restrict__ x, const float* __restrict__ w_in, const float* __restrict__ b_in, int64_t* __restrict__ ids,
                   int64_t tokens, int D, int bits) {
+  extern __shared__ float ws[];                    // [bits][D]
+  for (int i = threadIdx.x * 4; i < bits * D; i += blockDim.x * 4) *reinterpret_cast<float4*>(ws + i) = *reinterpret_cast<const float4*>(w_in + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t groups = (tokens + LFQ_TOK - 1) / LFQ_TOK;
+  for (int64_t g = (int64_t)blockIdx.x * 8 + warp; g < groups; g += (int64_t)gridDim.x * 8) {
+    const int64_t t0 = g * LFQ_TOK;
+    float acc[LFQ_TOK][BITS_MAX];
+#pragma unroll
+    for (int k = 0; k < LFQ_TOK; ++k)
+#pragma unroll
+      for (int i = 0; i < BITS_MAX; ++i) acc[k][i] = 0.f;
+#pragma unroll 2
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 xv[LFQ_TOK];
+#pragma unroll
+      for (int k = 0; k < LFQ_TOK; ++k) xv[k] = (t0 + k < tokens) ? lfq_load4<T>(x + (t0 + k) * D + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < BITS_MAX; ++i) {
+        if (i < bits) {
+          const float4 wv = *reinterpret_cast<const float4*>(ws + i * D + c);
+#pragma unroll
+          for (int k = 0; k < LFQ_TOK; ++k)
+            acc[k][i] = fmaf(xv[k].x, wv.x, fmaf(xv[k].y, wv.y, fmaf(xv[k].z, wv.z, fmaf(xv[k].w, wv.w, acc[k][i]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < LFQ_TOK; ++k) {
+      int64_t id = 0;
+#pragma unroll
+      for (int i = 0; i < BITS_MAX; ++i) {
+        if (i < bits) {
+          const float s = warp_sum(acc[k][i]) + (b_in ? __ldg(b_in + i) : 0.f);
+          if (s > 0.f) id |= (int64_t)1 << (bits - 1 - i);
+        }
+      }
+      if (lane == 0 && t0 + k < tokens) ids[t0 + k] = id;
+    }
+  }
+}
+
+// generic shapes (D % 4 != 0, identity projection): one warp per token, scalar loads
+template <typename T, int BITS_MAX>
+__global__ void __launch_bounds__(256)
+lfq_encode_generic_kernel(const T* __restrict__ x, const float* __restrict__ w_in, const float* __restrict__ b_in, int64_t* __restrict__ ids,
+                          int64_t tokens, int D, int bits) {
   extern __shared__ float ws[];                    // [bits][D]
   if (w_in) for (int i = threadIdx.x; i < bits * D; i += blockDim.x) ws[i] = w_in[i];
   __syncthreads();
@@ -155,24 +214,38 @@ vq_decode_codes_kernel(const int64_t* __restrict__ ids, const float* __restrict_
 
 using namespace mmg;
 
+template <typename T>
+static int launch_lfq(const mmg_vq_lfq_encode_args* a, cudaStream_t st) {
+  const size_t smem = a->w_in ? (size_t)a->bits * a->D * 4 : 0;
+  MMG_CHECK_ARG(smem <= 200 * 1024, "mmg_vq_lfq_encode: projection does not fit in shared memory");
+  const bool fast = a->w_in && a->D % 128 == 0 && (reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w_in) & 15) == 0;
+  const int per_block = fast ? 8 * LFQ_TOK : 8;
+  int64_t grid = (a->T + per_block - 1) / per_block; if (grid > (int64_t)num_sms()) grid = num_sms();      // the projection is staged once per CTA
+  auto launch = [&](auto kern) -> int {
+    MMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, 256, smem, st>>>((const T*)a->x, a->w_in, a->b_in, a->ids, a->T, a->D, a->bits);
+    MMG_LAUNCHED();
+    return MMG_OK;
+  };
+  if (fast) return a->bits <= 16 ? launch(lfq_encode_kernel<T, 16>) : launch(lfq_encode_kernel<T, 24>);
+  return launch(lfq_encode_generic_kernel<T, 24>);
+}
+
 extern "C" int mmg_vq_lfq_encode(const mmg_vq_lfq_encode_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MMG_CHECK_ARG(a && a->x && a->ids, "mmg_vq_lfq_encode: NULL pointer");
   MMG_CHECK_ARG(a->bits >= 1 && a->bits <= 24, "mmg_vq_lfq_encode: bits=%d not in [1,24]", a->bits);
   MMG_CHECK_ARG(a->w_in || a->D == a->bits, "mmg_vq_lfq_encode: identity projection needs D == bits");
   if (a->T == 0) return MMG_OK;
-  const size_t smem = a->w_in ? (size_t)a->bits * a->D * 4 : 0;
-  MMG_CHECK_ARG(smem <= 200 * 1024, "mmg_vq_lfq_encode: projection does not fit in shared memory");
-  int64_t grid = (a->T + 7) / 8; if (grid > (int64_t)num_sms() * 4) grid = (int64_t)num_sms() * 4;
-  if (a->dtype == MMG_BF16) {
-    MMG_CUDA(cudaFuncSetAttribute(lfq_encode_kernel<bf16, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lfq_encode_kernel<bf16, 24><<<(unsigned)grid, 256, smem, st>>>((const bf16*)a->x, a->w_in, a->b_in, a->ids, a->T, a->D, a->bits);
-  } else {
-    MMG_CUDA(cudaFuncSetAttribute(lfq_encode_kernel<float, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lfq_encode_kernel<float, 24><<<(unsigned)grid, 256, smem, st>>>((const float*)a->x, a->w_in, a->b_in, a->ids, a->T, a->D, a->bits);
+  if (a->dtype == MMG_BF16 && a->w_split && a->D % 64 == 0 && 3 * a->bits <= 64) {
+    // bf16 tokens: the projection runs on tcgen05 as ONE HBM-bound TMA stream of the tokens against the 3-way bf16 split of project_in
+    // ([hi | mid | lo] rows, hi + mid + lo == the fp32 weight), recombined in fp32 by the LFQ_IDS epilogue
+    mmg_linear_args l{};
+    l.a = a->x; l.w = a->w_split; l.M = a->T; l.N = 64; l.K = a->D; l.lda = a->D; l.ldw = a->D; l.dtype = MMG_BF16; l.epilogue = MMG_EPI_LFQ_IDS;
+    l.epi.out = a->ids; l.epi.ldo = 1; l.epi.out_dtype = MMG_F32; l.epi.bias = a->b_in; l.epi.ln_width = a->bits;
+    return mmg_linear(&l, stream);
   }
-  MMG_LAUNCHED();
-  return MMG_OK;
+  return a->dtype == MMG_BF16 ? launch_lfq<bf16>(a, st) : launch_lfq<float>(a, st);
 }
 
 extern "C" int mmg_vq_l2_argmin(const mmg_vq_l2_argmin_args* a, void* stream) {

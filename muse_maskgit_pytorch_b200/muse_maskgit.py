@@ -667,6 +667,29 @@ class MaskGit(nn.Module):
         self._aten_dev.copy_(torch.tensor([wrap(seed), off], dtype=torch.int64), non_blocking=False)
         return dict(key=(B, stride(ng), stride(nc), per_step), stride_g=stride(ng), stride_c=stride(nc), inc_g=inc(ng), per_step=per_step)
 
+    def _tail_buffers(self, b, n, rows_max, V, device):
+        """Scratch of the per-step sampling tail for at most `rows_max` sampled rows per sequence."""
+        tr = self.transformer
+        adt = tr._packed()["adt"]
+        return dict(e=torch.empty((b * n, tr.dim), device=device, dtype=adt),
+                    logits=torch.empty((b * rows_max, V), device=device, dtype=torch.float32))
+
+    def _sample_tail(self, x, nb, pos, rows_b, ids, scores, temp, step, u, cond_scale, k_keep, tail, seed_dev=None, only_masked_id=None, aten=None):
+        """The sampling tail of one decode step (muse_maskgit_pytorch.py:576-609) on the rows listed in `pos` (b, rows_b): final LayerNorm +
+        CFG combine in embedding space, to_logits, top-k filter, gumbel argmax, confidence score; ids / scores are updated in place.
+        x: residual stream [nb*b*n, dim] after the blocks (cond rows first, then the null-CFG rows)."""
+        tr = self.transformer
+        P = tr._packed()
+        b, n = ids.shape
+        bn = b * n
+        R = b * rows_b
+        e = tail["e"]
+        ops.final_embed(x[:bn], x[bn:2 * bn] if nb == 2 else None, P["gf"], pos, e, b, n, rows_b, cond_scale)
+        lg = tail["logits"][:R]
+        ops.linear(e[:R], P["wlog"], lg)
+        ops.logits_sample(lg, pos, ids, scores, rows_b, k_keep, temp, u=u, seed=0, seed_dev=seed_dev, step=step, row_offset=self.row_offset * n,
+                          only_masked_id=only_masked_id, aten=aten)
+
     def _generate_body(self, text_embeds, cond_images, *, fmap_size, temperature, topk_filter_thres, timesteps, cond_scale, b,
                        use_critic=False, critic_noise_scale=1., score_all=False, aten=None):
         """The device-side work of generate(): no host synchronisation, no data-dependent host control flow."""
@@ -690,8 +713,7 @@ class MaskGit(nn.Module):
                 and all("w2f" in l["ff"] for l in P["layers"])):
             native = self._native_step_setup(ctx, P, b, n, nb, max(sched), V, device)
         rows_max = n if score_all else max(sched)
-        e = torch.empty((b * n, tr.dim), device=device, dtype=adt) if native is None else None
-        logits = torch.empty((b * rows_max, V), device=device, dtype=torch.float32) if native is None else None
+        tail = self._tail_buffers(b, n, rows_max, V, device) if native is None else None
         all_pos = torch.arange(n, dtype=torch.int32, device=device).repeat(b, 1).contiguous() if score_all else None
         sc_embed = torch.empty((bn, tr.dim), device=device, dtype=torch.float32) if self.self_cond else None
         # token critic (muse_maskgit_pytorch.py:535-538, 590-600): a second stack over the freshly filled ids scores EVERY position
@@ -724,17 +746,13 @@ class MaskGit(nn.Module):
                 ops.layernorm(x[:bn], P["gf"], sc_embed)
             # rows that are sampled: the masked ones; every position when already-decoded tokens may be re-masked by confidence
             pos, rows_b = (all_pos, n) if score_all else (masked_pos, num_masked)
-            R = b * rows_b
-            ops.final_embed(x[:bn], x[bn:2 * bn] if nb == 2 else None, P["gf"], pos, e, b, n, rows_b, float(cond_scale))
-            lg = logits[:R]
-            ops.linear(e[:R], P["wlog"], lg)
             temp = temperature * (steps_until_x0 / timesteps)                  # annealed, muse_maskgit_pytorch.py:578
             u = None
             if self.sampler_noise_fn is not None:
                 u = self.sampler_noise_fn(step, (b, n, V)).to(device=device, dtype=torch.float32).contiguous()
             seed_dev = self._seed_dev if aten is None else self._aten_dev[0:1]
-            ops.logits_sample(lg, pos, ids, scores, rows_b, k_keep, float(temp), u=u, seed=0, seed_dev=seed_dev,
-                              step=step, row_offset=self.row_offset * n, only_masked_id=self.mask_id if score_all else None,
+            self._sample_tail(x, nb, pos, rows_b, ids, scores, float(temp), step, u, float(cond_scale), k_keep, tail, seed_dev=seed_dev,
+                              only_masked_id=self.mask_id if score_all else None,
                               aten=None if aten is None else (step * aten["per_step"], self._aten_dev[1:2], aten["stride_g"]))
             if use_critic:
                 xc = cnet._run_blocks(ids, cctx, cnb)

@@ -198,9 +198,11 @@ def ff_geglu(x, ln_gamma, w1, w2f, cvec, F, xn, h, stats, add=None, add_from=0):
     return x
 
 
-def vq_lfq_encode(x, w_in, b_in, ids, bits):
+def vq_lfq_encode(x, w_in, b_in, ids, bits, w_split=None):
+    """w_split: [64, D] bf16 3-way split of w_in -> bf16 tokens take the tcgen05 route (one TMA stream over the tokens)."""
     a = L.LfqEncodeArgs()
     a.x = _chk(x).data_ptr(); a.dtype = L.dt(x); a.w_in = L.ptr(w_in); a.b_in = L.ptr(b_in); a.ids = ids.data_ptr()
+    a.w_split = L.ptr(w_split)
     a.T = x.shape[0]; a.D = x.shape[1]; a.bits = bits
     L.call("mmg_vq_lfq_encode", a)
     return ids

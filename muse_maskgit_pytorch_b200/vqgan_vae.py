@@ -298,10 +298,8 @@ class VQGanVAE(nn.Module):
         P = self._packed()
         ids = torch.empty((x.shape[0],), device=x.device, dtype=torch.int64)
         if self.lookup_free_quantization:
-            if P["pin_w3"] is not None and x.dtype == torch.bfloat16:
-                ops.linear(x, P["pin_w3"], ids, epilogue=ops.EPI_LFQ_IDS, bias=P["pin_b"], ln_width=self.quantizer.bits)   # HBM-bound TMA stream of the fmap
-            else:
-                ops.vq_lfq_encode(x, P["pin_w"], P["pin_b"], ids, self.quantizer.bits)
+            # bf16 fmap + split projection: tcgen05 route inside mmg_vq_lfq_encode (HBM-bound TMA stream of the fmap); else CUDA cores
+            ops.vq_lfq_encode(x, P["pin_w"], P["pin_b"], ids, self.quantizer.bits, w_split=P["pin_w3"] if x.dtype == torch.bfloat16 else None)
         else:
             ids.fill_(-1)                                   # all-ones keys for the packed (distance, code) atomicMin
             ops.linear(x, P["codebook_a"], ids, epilogue=ops.EPI_ARGMIN, bias=P["code_norms"])
