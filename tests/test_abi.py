@@ -66,3 +66,17 @@ def test_decode_step_workspace_query_is_host_only():
     c3 = f(64, 2, 256, 512, 8, 1408, 65536, 256)
     assert c3 >= 64 * 256 * 65536 * 4 and c3 % 256 == 0
     assert f(8, 2, 256, 512, 8, 1408, 65536, 256) < c3 and f(0, 2, 256, 512, 8, 1408, 65536, 256) == 0
+
+
+def test_baseline_ref_is_the_unmodified_reference():
+    """baseline/_ref (the reference arm of bench.py) is byte-identical to /root/reference wherever both exist (build container)."""
+    import filecmp
+    import pytest
+    ref = "/root/reference/muse_maskgit_pytorch"
+    inst = os.path.join(ROOT, "baseline", "_ref", "muse_maskgit_pytorch")
+    if not (os.path.isdir(ref) and os.path.isdir(inst)):
+        pytest.skip("needs /root/reference and baseline/_ref")
+    names = sorted(f for f in os.listdir(ref) if f.endswith(".py"))
+    assert names and names == sorted(f for f in os.listdir(inst) if f.endswith(".py"))
+    match, mismatch, errors = filecmp.cmpfiles(ref, inst, names, shallow=False)
+    assert not mismatch and not errors, (mismatch, errors)
