@@ -185,6 +185,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": te_host.numel() * 4 * world, "d2h_bytes_per_step": host_out.numel() * 4},
             "gpu_launches": (launches if launches > 0 else roof["launches_per_step_all_kernels"]) * args.steps,   # graph replays re-issue the captured kernel nodes
             "launches_per_decode_step": round(roof["launches_per_step_all_kernels"] / TIMESTEPS, 1),
+            "simt_fallbacks": __import__("muse_maskgit_pytorch_b200")._lib.simt_fallback_count(),      # bf16 products that left the tcgen05 path (must be 0 here)
             "clocks": clocks,
             "roofline": roof,
             "dense_flop_frac_of_peak": round(value * GFLOP_PER_IMAGE / 1e3 / world / pk["tflops"], 4),
@@ -341,7 +342,7 @@ def teacher_forced_flip_rate(mg, b=2):
     O.generate_ids(sd, dict(heads=8, depth=8), te, n, V, lambda step, shape: torch.rand(shape, generator=g), timesteps=TIMESTEPS, cond_scale=COND_SCALE, trace=trace)
     t_or = time.perf_counter() - t0
     ctx = tr._prepare_context(te.cuda(), None, [False, True])
-    tail = mg._tail_buffers(b, n, n, V, torch.device("cuda"))
+    tail = mg._tail_buffers(b, n, n, V, torch.device("cuda"), math.ceil(0.1 * V))
     flips = total = 0
     for step, st in enumerate(trace):
         ids_in = st["ids_in"].cuda()
@@ -430,13 +431,14 @@ def cpu_baseline_port(cores):
 
 
 def gpu_eager_baseline(device):
-    """The unmodified reference modules on this B200 in eager PyTorch: fp32 (flash branch) and
-    autocast(bf16) with flash=False, global batch 64, one warm-up + one timed generate() each.  None of this repo's kernels run here."""
+    """The unmodified reference modules on this B200 in eager PyTorch: fp32 and autocast(bf16), both through
+    the reference-owned attention branch (flash=False, attend.py:123-138; the flash branch belongs to an un-vendored third-party package), global
+    batch 64, one warm-up + one timed generate() each.  None of this repo's kernels run here."""
     out = {}
     if not reference_available():
         return {"unavailable": "baseline/_ref missing"}
     te = text_embeddings(GLOBAL_BATCH).to(device)
-    for name, flash, autocast in (("fp32", True, False), ("autocast_bf16_flash_false", False, True)):
+    for name, flash, autocast in (("fp32", False, False), ("autocast_bf16", False, True)):
         try:
             mg = build_reference(device, flash=flash)
             torch.manual_seed(2)

@@ -39,6 +39,9 @@ int         mmg_version(void);
 const char* mmg_last_error(void);
 /* Number of kernel launches issued through this library by the calling process (bench.py "gpu_launches"). */
 int64_t     mmg_launch_count(void);
+/* Number of bf16 matrix products / convolutions of this process that fell off the tcgen05 path onto the CUDA-core kernel because of their shape
+ * or alignment (K or Cin % 64, N % 64, 16-byte rows, conv tile geometry).  MMG_VERBOSE=1 logs each one to stderr. */
+int64_t     mmg_simt_fallback_count(void);
 /* sizeof() of the argument block of entry point `name` ("mmg_linear", ...; "mmg_epilogue" for mmg_epilogue_args): lets a
  * foreign-language binding verify its struct mirror. Returns 0 for unknown names. */
 int         mmg_sizeof(const char* name);
@@ -238,8 +241,31 @@ typedef struct {
                                 word k&3 of Philox(counter = offset/4 + k/4, subsequence = t) * 2^-32 + 2^-33, 1 -> 0; aten_stride =
                                 256 * min(SMs * maxThreadsPerSM/256, ceil(numel/256)); accurate logf / IEEE division as with `u`  */
   uint64_t aten_offset; const uint64_t* aten_offset_dev; uint32_t aten_stride, _pad;
+  /* optional row indirection (the fallback leg of mmg_logits_fused): logits row j belongs to sampled row row_index[j] (the index into
+     masked_pos), only the first min(*row_count_dev, row_index_cap) rows are processed; the grid is row_index_cap CTAs               */
+  const int32_t* row_index; const int32_t* row_count_dev; int32_t row_index_cap, _pad2;
 } mmg_logits_sample_args;
 int mmg_logits_sample(const mmg_logits_sample_args* a, void* stream);
+
+/* to_logits + the sampling tail of a decode step in one call, WITHOUT a [rows, V] logits buffer (muse_maskgit_pytorch.py:576-609 on the rows
+ * listed in s.masked_pos; bf16 operands, tcgen05): a 4096-column sample GEMM gives every row a candidate threshold, the logits GEMM's epilogue
+ * keeps online-softmax partials and emits only the candidates >= threshold (~12 % of the logits) as per-row lists, a finishing kernel runs the
+ * exact-rank perturbed argmax of mmg_logits_sample on the lists.  Rows whose threshold missed are redone through materialised logits inside the
+ * same call (<= 128 rows per call; beyond that status[1] is raised and the caller must repeat the step with mmg_linear + mmg_logits_sample).
+ * Same results as mmg_linear + mmg_logits_sample up to the summation order of the softmax denominator.                                        */
+typedef struct {
+  const void* e;           /* [rows, K] bf16: mmg_final_embed output, rows = s.B * s.num_masked                                 */
+  const void* w;           /* [V, K] bf16 to_logits weight                                                                        */
+  int32_t K, _pad;
+  int64_t rows_capacity;   /* the R_max the workspace was sized for (0: rows of this call)                                        */
+  mmg_logits_sample_args s;/* sampler arguments as for mmg_logits_sample; s.logits / s.row_index are ignored                      */
+  void* workspace; uint64_t workspace_bytes;   /* >= mmg_logits_fused_workspace_bytes(rows_capacity, V, K, k), 256-byte aligned   */
+  int32_t* status;         /* device int32[2], zeroed by the caller: [0] += rows redone through the materialised fallback,
+                              [1] = 1 when a step had more such rows than the fallback holds (results of that step are incomplete)  */
+} mmg_logits_fused_args;
+/* 0 when the shape is not supported by the fused path (V % 256, V < 1024, K % 64, k too large for the candidate lists) */
+uint64_t mmg_logits_fused_workspace_bytes(int64_t rows_capacity, int32_t V, int32_t K, int32_t k);
+int mmg_logits_fused(const mmg_logits_fused_args* a, void* stream);
 
 /* token-critic scoring branch of MaskGit.generate (muse_maskgit_pytorch.py:590-600; TokenCritic :383-386, SelfCritic :352-361):
  *   s[r] = dot(LayerNorm(x_cond[r]) * gamma, w) + bias;   x_null != NULL: s = s_null + (s - s_null) * cond_scale  (CFG, :257)

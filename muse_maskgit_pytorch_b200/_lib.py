@@ -79,7 +79,13 @@ class LogitsSampleArgs(C.Structure):
     _fields_ = [("logits", vp), ("masked_pos", vp), ("ids", vp), ("scores", vp), ("u", vp),
                 ("B", i32), ("n", i32), ("num_masked", i32), ("V", i32), ("k", i32), ("temperature", f32),
                 ("seed", u64), ("step", u64), ("row_offset", i64), ("seed_dev", vp), ("mask_id", i64), ("only_masked", i32), ("rng_mode", i32),
-                ("aten_offset", u64), ("aten_offset_dev", vp), ("aten_stride", C.c_uint32), ("_pad", i32)]
+                ("aten_offset", u64), ("aten_offset_dev", vp), ("aten_stride", C.c_uint32), ("_pad", i32),
+                ("row_index", vp), ("row_count_dev", vp), ("row_index_cap", i32), ("_pad2", i32)]
+
+
+class LogitsFusedArgs(C.Structure):
+    _fields_ = [("e", vp), ("w", vp), ("K", i32), ("_pad", i32), ("rows_capacity", i64), ("s", LogitsSampleArgs),
+                ("workspace", vp), ("workspace_bytes", u64), ("status", vp)]
 
 
 class CriticScoreArgs(C.Structure):
@@ -133,9 +139,10 @@ EXPORTS = {
     "mmg_attention": AttentionArgs, "mmg_remask": RemaskArgs, "mmg_final_embed": FinalEmbedArgs,
     "mmg_logits_sample": LogitsSampleArgs, "mmg_vq_lfq_encode": LfqEncodeArgs, "mmg_vq_l2_argmin": L2ArgminArgs,
     "mmg_vq_decode_codes": DecodeCodesArgs, "mmg_cast": CastArgs, "mmg_critic_score": CriticScoreArgs,
-    "mmg_ff_geglu": FfGegluArgs, "mmg_decode_step": DecodeStepArgs,
+    "mmg_ff_geglu": FfGegluArgs, "mmg_decode_step": DecodeStepArgs, "mmg_logits_fused": LogitsFusedArgs,
 }
-PLAIN_EXPORTS = ("mmg_version", "mmg_last_error", "mmg_launch_count", "mmg_sizeof", "mmg_decode_step_workspace_bytes")
+PLAIN_EXPORTS = ("mmg_version", "mmg_last_error", "mmg_launch_count", "mmg_sizeof", "mmg_decode_step_workspace_bytes", "mmg_logits_fused_workspace_bytes",
+                 "mmg_simt_fallback_count")
 
 _lib = None
 
@@ -159,10 +166,13 @@ def lib():
         l.mmg_version.restype = C.c_int
         l.mmg_last_error.restype = C.c_char_p
         l.mmg_launch_count.restype = C.c_int64
+        l.mmg_simt_fallback_count.restype = C.c_int64
         l.mmg_sizeof.argtypes = [C.c_char_p]
         l.mmg_sizeof.restype = C.c_int
         l.mmg_decode_step_workspace_bytes.argtypes = [i32] * 8
         l.mmg_decode_step_workspace_bytes.restype = u64
+        l.mmg_logits_fused_workspace_bytes.argtypes = [i64, i32, i32, i32]
+        l.mmg_logits_fused_workspace_bytes.restype = u64
         for name, st in list(EXPORTS.items()) + [("mmg_epilogue", EpilogueArgs), ("mmg_attn_weights", AttnWeights), ("mmg_layer_weights", LayerWeights)]:
             if l.mmg_sizeof(name.encode()) != C.sizeof(st):
                 raise MMGError(f"ABI mismatch for {name}: C {l.mmg_sizeof(name.encode())} vs ctypes {C.sizeof(st)}")
@@ -181,6 +191,11 @@ def call(name, args, stream=None):
 
 def launch_count():
     return int(lib().mmg_launch_count())
+
+
+def simt_fallback_count():
+    """bf16 products that left the tcgen05 path for the CUDA-core kernel (shape / alignment): should stay 0 on the benchmark configs."""
+    return int(lib().mmg_simt_fallback_count())
 
 
 def dt(t):

@@ -21,6 +21,14 @@ inline int fail(int code, const char* fmt, ...) {
   return code;
 }
 inline std::atomic<int64_t>& launch_counter() { static std::atomic<int64_t> c{0}; return c; }
+// bf16 matrix products / convolutions that could not take the tcgen05 path (K or Cin % 64, N % 64, alignment, tile geometry) and ran on the
+// CUDA-core kernel instead: a >100x performance cliff, so it is counted (mmg_simt_fallback_count) and, with MMG_VERBOSE=1, logged once per shape
+inline std::atomic<int64_t>& simt_fallback_counter() { static std::atomic<int64_t> c{0}; return c; }
+inline void note_simt_fallback(const char* what, long long M, long long N, long long K) {
+  simt_fallback_counter()++;
+  static const bool verbose = [] { const char* e = getenv("MMG_VERBOSE"); return e && e[0] == '1'; }();
+  if (verbose) fprintf(stderr, "[libmmg] %s M=%lld N=%lld K=%lld (bf16) runs on the CUDA-core kernel: shape / alignment outside the tcgen05 path\n", what, M, N, K);
+}
 
 #define MMG_CHECK_ARG(cond, ...) do { if (!(cond)) return ::mmg::fail(MMG_EINVAL, __VA_ARGS__); } while (0)
 #define MMG_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \

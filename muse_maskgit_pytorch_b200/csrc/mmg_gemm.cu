@@ -5,6 +5,8 @@
 
 namespace mmg {
 
+int linear_impl(const mmg_linear_args* a, const int* skip_if_zero, void* stream);
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int BN>
@@ -297,7 +299,10 @@ static int tile_geometry(int Ho, int Wo, TcGemmParams* p) {
 
 using namespace mmg;
 
-extern "C" int mmg_linear(const mmg_linear_args* a, void* stream) {
+extern "C" int mmg_linear(const mmg_linear_args* a, void* stream) { return mmg::linear_impl(a, nullptr, stream); }
+
+// skip_if_zero: optional device word; the tensor-core kernel returns at once when it reads 0 there (the fallback leg of mmg_logits_fused)
+int mmg::linear_impl(const mmg_linear_args* a, const int* skip_if_zero, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MMG_CHECK_ARG(a && a->a && a->w, "mmg_linear: NULL operand");
   MMG_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "mmg_linear: bad shape M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K);
@@ -306,11 +311,14 @@ extern "C" int mmg_linear(const mmg_linear_args* a, void* stream) {
   const bool tc_ok = a->dtype == MMG_BF16 && (a->K % 64 == 0) && (a->N % 64 == 0) && (a->lda % 8 == 0) && (a->ldw % 8 == 0) &&
                      aligned16(a->a) && aligned16(a->w) && (a->epi.ldo % 8 == 0 || a->epilogue == MMG_EPI_QKV || a->epilogue == MMG_EPI_CONVT_RGB || a->epilogue == MMG_EPI_LFQ_IDS || a->epilogue == MMG_EPI_ARGMIN);
   if (!tc_ok) {
+    MMG_CHECK_ARG(!skip_if_zero, "skippable GEMM requires the bf16 tensor-core path");
+    if (a->dtype == MMG_BF16) note_simt_fallback("mmg_linear", a->M, a->N, a->K);
     MMG_CHECK_ARG(!a->epi.ln_out, "fused LayerNorm output requires the bf16 tensor-core path (K %% 64, N %% 64, aligned operands)");
     ConvGeom g{};
     return launch_simt<false>(a->dtype, a->a, a->w, a->M, a->N, a->K, a->lda, a->ldw, g, epi, st);
   }
   TcGemmParams p{};
+  p.skip_if_zero = skip_if_zero;
   p.M = a->M; p.N = a->N; p.num_kb = (int)(a->K / TC_BK); p.mode = 0;
   p.num_m_tiles = (int)((a->M + TC_BM - 1) / TC_BM);
   p.epi = epi; p.epi.fast = 1;
@@ -344,7 +352,10 @@ extern "C" int mmg_conv2d(const mmg_conv2d_args* a, void* stream) {
   TcGemmParams p{};
   const bool tc_ok = a->dtype == MMG_BF16 && a->kind != 3 && (a->Cin % 64 == 0) && (N % 64 == 0) && aligned16(a->x) && aligned16(a->w) &&
                      (a->epi.ldo % 8 == 0) && tile_geometry(g.Ho, g.Wo, &p) == 0;
-  if (!tc_ok) return launch_simt<true>(a->dtype, a->x, a->w, M, N, K, 0, K, g, epi, st);
+  if (!tc_ok) {
+    if (a->dtype == MMG_BF16) note_simt_fallback("mmg_conv2d", M, N, K);
+    return launch_simt<true>(a->dtype, a->x, a->w, M, N, K, 0, K, g, epi, st);
+  }
   p.M = M; p.N = N; p.mode = 1; p.cchunks = a->Cin / 64; p.ntaps = g.ntaps; p.num_kb = p.ntaps * p.cchunks;
   p.Ho = g.Ho; p.Wo = g.Wo; p.B = a->B;
   p.num_m_tiles = p.tiles_x * p.tiles_y * ((a->B + p.TB - 1) / p.TB);
@@ -385,6 +396,7 @@ extern "C" int mmg_conv_transpose2d(const mmg_conv_transpose2d_args* a, void* st
                      (a->epilogue == MMG_EPI_CONVT_RGB ? (N == 64 || N == 128 || N == 256) : (a->epi.ldo % 8 == 0)) &&
                      tile_geometry(a->H, a->W, &p) == 0;
   const size_t esz = a->dtype == MMG_BF16 ? 2 : 4;
+  if (!tc_ok && a->dtype == MMG_BF16) note_simt_fallback("mmg_conv_transpose2d", M, N, K);
   for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px) {
     Epilogue epi; epi.p = a->epi; epi.kind = a->epilogue; epi.fast = 0; epi.M = M; epi.N = N;
     epi.p.H = a->H; epi.p.W = a->W; epi.p.py = py; epi.p.px = px;

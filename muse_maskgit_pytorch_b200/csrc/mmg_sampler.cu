@@ -11,78 +11,9 @@
 //      else excluded and repeated.  This equals argmax over torch.topk's kept set without ever forming the set.
 //   If the list would miss the top-k (count < k) or overflow, an exact bitwise radix descent over the L2-resident
 //   row finds the k-th largest key and the list is rebuilt (rare; exercised by the tests with adversarial rows).
-#include "mmg_common.cuh"
-#include <float.h>
+#include "mmg_sampler.cuh"
 
 namespace mmg {
-
-constexpr int SMP_THREADS = 512;
-constexpr int SMP_SAMPLE = 4096;
-constexpr int SMP_CAP = 9216;
-
-__device__ __forceinline__ uint32_t fkey(float x) {           // order-preserving float -> uint32
-  const uint32_t u = __float_as_uint(x);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ld_stream(const float* p) {
-  float v; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
-}
-__device__ __forceinline__ float4 ld_stream4(const float4* p) {
-  float4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return v;
-}
-
-// Philox4x32-10, counter = (v, step, row_lo, row_hi), key = seed; returns the first output word.
-__device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;     // one IMAD.WIDE each
-    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  return c0;
-}
-
-// Philox4x32-10, all four output words
-__device__ __forceinline__ uint4 philox4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
-    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  return make_uint4(c0, c1, c2, c3);
-}
-
-// The value ATen's CUDA `uniform_(0, 1)` writes at flat index t + stride * k of an fp32 tensor (generator seed / offset):
-// word (k & 3) of Philox(counter = offset/4 + (k >> 2), subsequence = t), mapped like curand_uniform4 (w * 2^-32 + 2^-33, in
-// (0, 1]) and then 1 -> 0.  (DistributionTemplates.h: distribution_elementwise_grid_stride_kernel + uniform_kernel.)
-__device__ __forceinline__ float aten_uniform(uint32_t t, uint64_t k, uint64_t off4, uint64_t seed) {
-  const uint64_t ctr = off4 + (k >> 2);
-  const uint4 w4 = philox4((uint32_t)ctr, (uint32_t)(ctr >> 32), t, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
-  const uint32_t ii = (uint32_t)k & 3u;
-  const uint32_t w = ii == 0 ? w4.x : ii == 1 ? w4.y : ii == 2 ? w4.z : w4.w;
-  const float u = fmaf(__uint2float_rn(w), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  return u == 1.0f ? 0.0f : u;
-}
-
-__device__ __forceinline__ bool better(float v, int vi, float w, int wi) { return v > w || (v == w && vi < wi); }
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float key_to_float(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
-
-// block-wide sum of two packed counters (each < 2^15), one __syncthreads pair; result broadcast to every thread
-__device__ __forceinline__ void block_sum2(int a, int b, int* red, int warp, int lane, int& oa, int& ob) {
-  a = __reduce_add_sync(0xffffffffu, a); b = __reduce_add_sync(0xffffffffu, b);
-  __syncthreads();
-  if (lane == 0) { red[warp] = a; red[32 + warp] = b; }
-  __syncthreads();
-  oa = 0; ob = 0;
-#pragma unroll
-  for (int w = 0; w < SMP_THREADS / 32; ++w) { oa += red[w]; ob += red[32 + w]; }
-}
 
 // MODE 1 = injected-noise parity mode, MODE 2 = ATen-compatible in-kernel Philox (the stream a seeded torch.cuda run of the
 // reference draws): IEEE division and accurate logf so the perturbed values match the reference's fp32 arithmetic as closely
@@ -95,17 +26,20 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   int* lidx = reinterpret_cast<int*>(lval + SMP_CAP);            // [SMP_CAP] candidate vocabulary indices
   float4* scr = reinterpret_cast<float4*>(lidx + SMP_CAP);       // [4][SMP_THREADS] per-thread staging of the 16 values in flight
   __shared__ int s_count, s_n;
-  __shared__ int s_red[64];
-  __shared__ float s_redf[32]; __shared__ int s_redi[32]; __shared__ int s_redj[32];
+  __shared__ SampleScratch sc;
   __shared__ float s_max, s_sum;
 
   pdl_wait(); pdl_trigger();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = a.V, k = a.k;
-  const int64_t r = blockIdx.x;
+  int64_t r = blockIdx.x;
+  const float* row = a.logits + r * (int64_t)V;
+  if (a.row_index) {                                  // fallback leg of mmg_logits_fused: logits row j belongs to sampled row row_index[j]
+    if ((int)blockIdx.x >= *a.row_count_dev) return;
+    r = a.row_index[blockIdx.x];
+  }
   const int b = (int)(r / a.num_masked);
   const int pos = a.masked_pos[r];
-  const float* row = a.logits + r * (int64_t)V;
 
   // ---------------- phase A: sample (registers) -> provisional threshold ----------------
   const int ns = V < SMP_SAMPLE ? V : SMP_SAMPLE;
@@ -125,47 +59,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
     }
   }
   if (tid == 0) s_count = 0;
-  float tlo;
-  if (ns == V) {
-    // small rows: the "sample" is the whole row -> exact k-th largest by a block-wide radix descent (two key bits per round)
-    const int rs = k < ns ? k : ns;
-    uint32_t prefix = 0;
-    for (int bit = 30; bit >= 0; bit -= 2) {
-      const uint32_t c1 = prefix | (1u << bit), c2 = prefix | (2u << bit), c3 = prefix | (3u << bit);
-      int n1 = 0, n2 = 0, n3 = 0;
-#pragma unroll
-      for (int j = 0; j < SPT; ++j) { n1 += (sk[j] >= c1); n2 += (sk[j] >= c2); n3 += (sk[j] >= c3); }
-      int t12, t3;
-      block_sum2(n1 | (n2 << 16), n3, s_red, warp, lane, t12, t3);
-      const int t1 = t12 & 0xffff, t2 = t12 >> 16;
-      if (t3 >= rs) prefix = c3; else if (t2 >= rs) prefix = c2; else if (t1 >= rs) prefix = c1;
-    }
-    tlo = key_to_float(prefix);
-    if (prefix == 0) tlo = -FLT_MAX;
-  } else {
-    // sampled rows: every warp finds the rank-(rs/16) key of ITS 256 samples with shuffles only (no block barrier), the block
-    // threshold is the mean of the 16 warp estimates (same variance as one 4096-sample quantile; exactness is restored below)
-    const float pf = (float)k / (float)V; const float mu = pf * ns;
-    const int rs = (int)(mu + 4.0f * sqrtf(mu * (1.f - pf)) + 2.f);
-    const int rw = (rs + SMP_THREADS / 32 - 1) / (SMP_THREADS / 32);
-    uint32_t prefix = 0;
-    for (int bit = 30; bit >= 12; bit -= 2) {                          // 20 key bits are plenty for a lower bound
-      const uint32_t c1 = prefix | (1u << bit), c2 = prefix | (2u << bit), c3 = prefix | (3u << bit);
-      int n = 0;
-#pragma unroll
-      for (int j = 0; j < SPT; ++j) n += (sk[j] >= c1) + ((sk[j] >= c2) << 10) + ((sk[j] >= c3) << 20);
-      n = __reduce_add_sync(0xffffffffu, n);
-      const int t1 = n & 1023, t2 = (n >> 10) & 1023, t3 = n >> 20;
-      if (t3 >= rw) prefix = c3; else if (t2 >= rw) prefix = c2; else if (t1 >= rw) prefix = c1;
-    }
-    if (lane == 0) s_redf[warp] = prefix ? key_to_float(prefix) : -FLT_MAX;
-    __syncthreads();
-    float acc = 0.f; bool bad = false;
-#pragma unroll
-    for (int w = 0; w < SMP_THREADS / 32; ++w) { const float t = s_redf[w]; bad |= (t == -FLT_MAX) | !(t == t); acc += t; }
-    tlo = bad ? -FLT_MAX : acc * (1.0f / (SMP_THREADS / 32));
-    __syncthreads();
-  }
+  const float tlo = sample_threshold(sk, ns, V, k, sc, warp, lane);
   const bool degenerate = (tlo == -FLT_MAX);                         // no usable threshold: every element is a candidate (-> exact rebuild)
 
   // ---------------- phase B: one streaming pass over the row ----------------
@@ -278,16 +172,16 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   {
     float m = warp_max(m_t);
     __syncthreads();
-    if (lane == 0) s_redf[warp] = m;
+    if (lane == 0) sc.redf[warp] = m;
     __syncthreads();
-    float M = s_redf[lane % (SMP_THREADS / 32)];
+    float M = sc.redf[lane % (SMP_THREADS / 32)];
     M = warp_max(M);
     float sm = s_t * ex2_approx((m_t - M) * LOG2E);
     sm = warp_sum(sm);
     __syncthreads();
-    if (lane == 0) s_redf[warp] = sm;
+    if (lane == 0) sc.redf[warp] = sm;
     __syncthreads();
-    if (tid == 0) { float t = 0.f; for (int w = 0; w < SMP_THREADS / 32; ++w) t += s_redf[w]; s_sum = t; s_max = M; s_n = s_count; }
+    if (tid == 0) { float t = 0.f; for (int w = 0; w < SMP_THREADS / 32; ++w) t += sc.redf[w]; s_sum = t; s_max = M; s_n = s_count; }
     __syncthreads();
   }
   int n = s_n;
@@ -300,7 +194,7 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
       int c = 0;
       for (int i = tid; i < V; i += SMP_THREADS) c += (fkey(row[i]) >= cand);
       int tot, dummy;
-      block_sum2(c, 0, s_red, warp, lane, tot, dummy);
+      block_sum2(c, 0, sc.red, warp, lane, tot, dummy);
       if (tot >= k) prefix = cand;
     }
     // list = all keys > prefix (fewer than k of them), then ties (== prefix) in index order until k entries
@@ -336,71 +230,8 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
   }
 
   // ---------------- phase C: perturbed argmax restricted to the exact top-k ----------------
-  const int64_t grow = a.row_offset + (int64_t)b * a.n + pos;
-  const uint64_t seed = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
-  const float inv_t = 1.0f / tdiv;
-  uint64_t aq0 = 0, aoff4 = 0; uint32_t ar0 = 0;
-  if (MODE == 2) {            // flat index of logit (grow, v) in the reference's [B, n, V] noise tensor = grow * V + v = ar0 + v + S * aq0
-    const uint64_t base = (uint64_t)grow * (uint64_t)V;
-    aq0 = base / a.aten_stride; ar0 = (uint32_t)(base - aq0 * a.aten_stride);
-    aoff4 = (a.aten_offset + (a.aten_offset_dev ? *a.aten_offset_dev : 0ull)) >> 2;
-  }
-  constexpr int PER = (SMP_CAP + SMP_THREADS - 1) / SMP_THREADS;
-  float pv[PER];
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    const int s = tid + j * SMP_THREADS;
-    float p = -FLT_MAX;
-    if (s < n) {
-      const int v = lidx[s];
-      if (MODE != 0) {
-        float u;
-        if (MODE == 1) u = a.u[((int64_t)b * a.n + pos) * V + v];
-        else { const uint32_t r = ar0 + (uint32_t)v, dq = r / a.aten_stride; u = aten_uniform(r - dq * a.aten_stride, aq0 + dq, aoff4, seed); }
-        const float l1 = logf(fmaxf(u, 1e-20f));
-        p = __fdiv_rn(lval[s], tdiv) - logf(fmaxf(-l1, 1e-20f));
-      } else {
-        const float u = (float)(philox_first((uint32_t)v, (uint32_t)a.step, (uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), (uint32_t)seed, (uint32_t)(seed >> 32)) >> 8) * (1.0f / 16777216.0f);
-        const float l1 = __logf(fmaxf(u, 1e-20f));
-        p = fmaf(lval[s], inv_t, -__logf(fmaxf(-l1, 1e-20f)));
-      }
-    }
-    pv[j] = p;
-  }
-  int win_v = -1; float win_x = 0.f;
-  for (int iter = 0; iter < n; ++iter) {
-    // block argmax of the perturbed value (ties -> lowest vocabulary index)
-    float bv = -FLT_MAX; int bi = 0x7fffffff, bs = -1;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const int s = tid + j * SMP_THREADS;
-      if (s < n) { const int vi = lidx[s]; if (bs < 0 || better(pv[j], vi, bv, bi)) { bv = pv[j]; bi = vi; bs = s; } }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o); const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-      if (os >= 0 && (bs < 0 || better(ov, oi, bv, bi))) { bv = ov; bi = oi; bs = os; }
-    }
-    __syncthreads();
-    if (lane == 0) { s_redf[warp] = bv; s_redi[warp] = bi; s_redj[warp] = bs; }
-    __syncthreads();
-    bv = s_redf[0]; bi = s_redi[0]; bs = s_redj[0];
-#pragma unroll
-    for (int w = 1; w < SMP_THREADS / 32; ++w) {
-      const float ov = s_redf[w]; const int oi = s_redi[w], os = s_redj[w];
-      if (os >= 0 && (bs < 0 || better(ov, oi, bv, bi))) { bv = ov; bi = oi; bs = os; }
-    }
-    // exact rank of the candidate inside the row (the list covers everything >= its value)
-    const float cx = lval[bs];
-    int c = 0;
-    for (int s = tid; s < n; s += SMP_THREADS) { const float x = lval[s]; c += (x > cx) || (x == cx && lidx[s] < bi); }
-    int rank, dummy;
-    block_sum2(c, 0, s_red, warp, lane, rank, dummy);
-    if (rank < k) { win_v = bi; win_x = cx; break; }
-    // not in the kept set: drop its perturbed value (its logit stays in the list for later rank computations)
-#pragma unroll
-    for (int j = 0; j < PER; ++j) if (tid + j * SMP_THREADS == bs) pv[j] = -FLT_MAX;
-  }
+  int win_v; float win_x;
+  sample_from_list<MODE>(a, tdiv, lval, lidx, n, k, V, b, pos, sc, tid, warp, lane, win_v, win_x);
   if (tid == 0) {
     if (win_v < 0) { win_v = 0; win_x = row[0]; }                 // degenerate rows (all -inf / NaN)
     const float p = expf(win_x - s_max) / s_sum;
@@ -499,7 +330,8 @@ extern "C" int mmg_logits_sample(const mmg_logits_sample_args* a, void* stream) 
   MMG_CHECK_ARG(a && a->logits && a->masked_pos && a->ids && a->scores, "mmg_logits_sample: NULL pointer");
   MMG_CHECK_ARG(a->V >= 32 && a->V % 32 == 0, "mmg_logits_sample: V=%d must be a positive multiple of 32", a->V);
   MMG_CHECK_ARG(a->k >= 1 && a->k <= a->V && a->k <= SMP_CAP, "mmg_logits_sample: k=%d out of range (<= %d)", a->k, SMP_CAP);
-  const int64_t R = (int64_t)a->B * a->num_masked;
+  MMG_CHECK_ARG(!a->row_index || (a->row_count_dev && a->row_index_cap > 0), "mmg_logits_sample: row_index needs row_count_dev and row_index_cap");
+  const int64_t R = a->row_index ? a->row_index_cap : (int64_t)a->B * a->num_masked;
   if (R == 0) return MMG_OK;
   static const size_t smem = (size_t)SMP_CAP * 8 + (size_t)SMP_THREADS * 64;
   MMG_CHECK_ARG(a->rng_mode == 0 || (a->rng_mode == 1 && a->aten_stride >= 256 && a->aten_stride % 256 == 0 && a->aten_offset % 4 == 0 && !a->u),

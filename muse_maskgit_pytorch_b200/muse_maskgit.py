@@ -503,6 +503,9 @@ class MaskGit(nn.Module):
         self.global_batch = None            # "aten" + batch sharding: size of the whole batch the reference would have drawn noise for
         self.use_cuda_graph = True
         self.use_native_step = False        # True: one mmg_decode_step call per step (the same launch sequence issued from C++)
+        self.check_fused_tail = True        # read the fused path's overflow word after every call (4 bytes, one host sync)
+        self.last_fused_fallback_rows = 0   # rows of the last generate() that were redone through materialised logits (diagnostic)
+        self.use_fused_tail = True          # bf16: to_logits + sampling tail without materialised logits (mmg_logits_fused); False: mmg_linear + mmg_logits_sample
         self._graphs = {}
         self.row_offset = 0                 # global index of this shard's first sequence (multi-GPU batch sharding)
         self.register_load_state_dict_post_hook(lambda m, _inc: m._graphs.clear())
@@ -576,13 +579,16 @@ class MaskGit(nn.Module):
                        score_all=bool(can_remask_prev_masked) and not use_critic, aten=aten)
         critic_net = self.token_critic if isinstance(self.token_critic, Transformer) and use_critic else None
         if not self.use_cuda_graph or self.sampler_noise_fn is not None:
-            images, ids = body(text_embeds, cond_images)
+            images, ids, status = body(text_embeds, cond_images)
+            if self._fused_tail_overflowed(status):
+                return self._generate_unfused(texts, negative_texts, cond_images, fmap_size, temperature, topk_filter_thres, can_remask_prev_masked,
+                                              force_not_use_token_critic, timesteps, cond_scale, critic_noise_scale, return_ids)
             return (images, ids) if return_ids else images
         # ---- whole-call CUDA graph: 18 decode steps + VAE decode replayed as one launch (no per-kernel host work) ----
         key = (b, tuple(text_embeds.shape), text_embeds.dtype, None if cond_images is None else tuple(cond_images.shape), fmap_size,
                float(temperature), float(topk_filter_thres), int(timesteps), float(cond_scale), int(self.row_offset), tr.precision, self.vae.precision,
                use_critic, float(critic_noise_scale), bool(can_remask_prev_masked), None if aten is None else aten["key"], bool(self.use_native_step),
-               id(self.noise_schedule), os.environ.get("MMG_FUSE_LN", "0"))
+               id(self.noise_schedule), os.environ.get("MMG_FUSE_LN", "0"), bool(self.use_fused_tail))
         pack_ids = lambda: (id(tr._pack), id(self.vae._pack), id(self.cond_vae._pack), id(critic_net._pack) if critic_net is not None else 0,
                             id(self.token_critic._head_cache) if isinstance(self.token_critic, SelfCritic) else 0)
         entry = self._graphs.get(key)
@@ -595,9 +601,9 @@ class MaskGit(nn.Module):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out_images, out_ids = body(te_s, ci_s)
+                out_images, out_ids, out_status = body(te_s, ci_s)
             # the entry keeps alive everything the captured kernels point at (packed weights, workspaces)
-            entry = (graph, te_s, ci_s, out_images, out_ids, pack_ids(),
+            entry = (graph, te_s, ci_s, out_images, (out_ids, out_status), pack_ids(),
                      (tr._pack, self.vae._pack, self.cond_vae._pack, dict(getattr(tr, "_ws", {})),
                       None if critic_net is None else (critic_net._pack, dict(getattr(critic_net, "_ws", {}))),
                       self.token_critic._head_cache if isinstance(self.token_critic, SelfCritic) else None))
@@ -605,13 +611,35 @@ class MaskGit(nn.Module):
                 self._graphs.pop(next(iter(self._graphs)))       # least recently used (hits are moved to the end below)
         self._graphs.pop(key, None)
         self._graphs[key] = entry
-        graph, te_s, ci_s, out_images, out_ids = entry[:5]
+        graph, te_s, ci_s, out_images, (out_ids, out_status) = entry[:5]
         te_s.copy_(text_embeds, non_blocking=True)
         if ci_s is not None:
             ci_s.copy_(cond_images, non_blocking=True)
         graph.replay()
         images, ids = out_images.clone(), out_ids.clone()
+        if self._fused_tail_overflowed(out_status):
+            return self._generate_unfused(texts, negative_texts, cond_images, fmap_size, temperature, topk_filter_thres, can_remask_prev_masked,
+                                          force_not_use_token_critic, timesteps, cond_scale, critic_noise_scale, return_ids)
         return (images, ids) if return_ids else images
+
+    def _fused_tail_overflowed(self, status):
+        """status[1] != 0: some decode step had more rows whose sampled top-k threshold missed than the fused path's fallback holds (e.g. constant
+        logits rows).  One 4-byte read per call; `check_fused_tail = False` skips it (and the host synchronisation it implies)."""
+        if status is None or not self.check_fused_tail:
+            return False
+        self.last_fused_fallback_rows, overflow = (int(v) for v in status.tolist())
+        return overflow != 0
+
+    def _generate_unfused(self, *args):
+        saved = self.use_fused_tail
+        self.use_fused_tail = False
+        try:
+            if self.sampler_rng == "aten" and self.sampler_noise_fn is None:       # re-read the generator position the failed attempt consumed
+                gen = torch.cuda.default_generators[next(self.parameters()).device.index or 0]
+                gen.set_offset(self._aten_start_offset)
+            return self._generate(*args)
+        finally:
+            self.use_fused_tail = saved
 
     def _native_step_setup(self, ctx, P, b, n, nb, max_masked, V, device):
         """Argument block of mmg_decode_step for this generate(): the packed weights and the per-call context as raw pointers, plus the
@@ -660,6 +688,7 @@ class MaskGit(nn.Module):
         ng, nc = B * n * V, B * n
         per_step = inc(ng) + (inc(nc) if use_critic else 0)
         seed, off = gen.initial_seed(), gen.get_offset()
+        self._aten_start_offset = off
         gen.set_offset(off + timesteps * per_step)
         if getattr(self, "_aten_dev", None) is None or self._aten_dev.device != device:
             self._aten_dev = torch.zeros((2,), dtype=torch.int64, device=device)
@@ -667,12 +696,21 @@ class MaskGit(nn.Module):
         self._aten_dev.copy_(torch.tensor([wrap(seed), off], dtype=torch.int64), non_blocking=False)
         return dict(key=(B, stride(ng), stride(nc), per_step), stride_g=stride(ng), stride_c=stride(nc), inc_g=inc(ng), per_step=per_step)
 
-    def _tail_buffers(self, b, n, rows_max, V, device):
-        """Scratch of the per-step sampling tail for at most `rows_max` sampled rows per sequence."""
+    def _tail_buffers(self, b, n, rows_max, V, device, k_keep=None):
+        """Scratch of the per-step sampling tail for at most `rows_max` sampled rows per sequence.  bf16 + a supported shape: the workspace of
+        the fused logits / sampling path (candidate lists, no [rows, V] logits); otherwise the materialised fp32 logits."""
         tr = self.transformer
         adt = tr._packed()["adt"]
-        return dict(e=torch.empty((b * n, tr.dim), device=device, dtype=adt),
-                    logits=torch.empty((b * rows_max, V), device=device, dtype=torch.float32))
+        bufs = dict(e=torch.empty((b * n, tr.dim), device=device, dtype=adt), rows_max=rows_max)
+        nbytes = 0
+        if self.use_fused_tail and adt == torch.bfloat16 and k_keep is not None and os.environ.get("MMG_FUSED_TAIL", "1") != "0":
+            nbytes = ops.logits_fused_workspace_bytes(b * rows_max, V, tr.dim, k_keep)
+        if nbytes:
+            bufs["fused_ws"] = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+            bufs["status"] = torch.zeros((2,), dtype=torch.int32, device=device)
+        else:
+            bufs["logits"] = torch.empty((b * rows_max, V), device=device, dtype=torch.float32)
+        return bufs
 
     def _sample_tail(self, x, nb, pos, rows_b, ids, scores, temp, step, u, cond_scale, k_keep, tail, seed_dev=None, only_masked_id=None, aten=None):
         """The sampling tail of one decode step (muse_maskgit_pytorch.py:576-609) on the rows listed in `pos` (b, rows_b): final LayerNorm +
@@ -685,10 +723,14 @@ class MaskGit(nn.Module):
         R = b * rows_b
         e = tail["e"]
         ops.final_embed(x[:bn], x[bn:2 * bn] if nb == 2 else None, P["gf"], pos, e, b, n, rows_b, cond_scale)
+        kw = dict(u=u, seed=0, seed_dev=seed_dev, step=step, row_offset=self.row_offset * n, only_masked_id=only_masked_id, aten=aten)
+        if "fused_ws" in tail:      # logits never reach HBM: candidate lists out of the GEMM epilogue, sampled by the finishing kernel
+            ops.logits_fused(e[:R], P["wlog"], pos, ids, scores, rows_b, k_keep, temp, tail["fused_ws"], tail["status"],
+                             rows_capacity=b * tail["rows_max"], **kw)
+            return
         lg = tail["logits"][:R]
         ops.linear(e[:R], P["wlog"], lg)
-        ops.logits_sample(lg, pos, ids, scores, rows_b, k_keep, temp, u=u, seed=0, seed_dev=seed_dev, step=step, row_offset=self.row_offset * n,
-                          only_masked_id=only_masked_id, aten=aten)
+        ops.logits_sample(lg, pos, ids, scores, rows_b, k_keep, temp, **kw)
 
     def _generate_body(self, text_embeds, cond_images, *, fmap_size, temperature, topk_filter_thres, timesteps, cond_scale, b,
                        use_critic=False, critic_noise_scale=1., score_all=False, aten=None):
@@ -713,7 +755,7 @@ class MaskGit(nn.Module):
                 and all("w2f" in l["ff"] for l in P["layers"])):
             native = self._native_step_setup(ctx, P, b, n, nb, max(sched), V, device)
         rows_max = n if score_all else max(sched)
-        tail = self._tail_buffers(b, n, rows_max, V, device) if native is None else None
+        tail = self._tail_buffers(b, n, rows_max, V, device, k_keep) if native is None else None
         all_pos = torch.arange(n, dtype=torch.int32, device=device).repeat(b, 1).contiguous() if score_all else None
         sc_embed = torch.empty((bn, tr.dim), device=device, dtype=torch.float32) if self.self_cond else None
         # token critic (muse_maskgit_pytorch.py:535-538, 590-600): a second stack over the freshly filled ids scores EVERY position
@@ -728,7 +770,12 @@ class MaskGit(nn.Module):
                 whead, bhead = cnet._packed()["whead"], 0.
                 assert whead is not None, "token_critic must have dim_out == 1"
             gcrit = cnet._packed()["gf"]
+        nvtx = os.environ.get("MMG_NVTX", "0") == "1"            # host-side NVTX ranges per decode step / stage (visible in nsys / ncu --nvtx)
         for step, (num_masked, steps_until_x0) in enumerate(zip(sched, reversed(range(timesteps)))):
+            if nvtx:
+                if step:
+                    torch.cuda.nvtx.range_pop()
+                torch.cuda.nvtx.range_push(f"mmg.decode_step[{step}] masked={num_masked}")
             if native is not None:
                 u = None
                 if self.sampler_noise_fn is not None:
@@ -764,8 +811,13 @@ class MaskGit(nn.Module):
                                  step=step, row_offset=self.row_offset * n,
                                  aten=None if aten is None else (step * aten["per_step"] + aten["inc_g"], self._aten_dev[1:2], aten["stride_c"]))
         ids = ids.view(b, fmap_size, fmap_size)
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
+            torch.cuda.nvtx.range_push("mmg.vae_decode")
         images = self.vae.decode_from_ids(ids)
-        return images, ids
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
+        return images, ids, (tail.get("status") if tail is not None else None)
 
     def forward(self, *args, **kwargs):
         raise NotImplementedError("MaskGit.forward is the training loss (muse_maskgit_pytorch.py:623-741); training is out of scope")

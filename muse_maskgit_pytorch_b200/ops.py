@@ -171,6 +171,29 @@ def logits_sample(logits, masked_pos, ids, scores, num_masked, k, temperature, u
     L.call("mmg_logits_sample", a)
 
 
+def logits_fused_workspace_bytes(rows_capacity, V, K, k):
+    """Bytes of workspace mmg_logits_fused needs for up to `rows_capacity` sampled rows; 0 = shape not supported by the fused path."""
+    return int(L.lib().mmg_logits_fused_workspace_bytes(int(rows_capacity), int(V), int(K), int(k)))
+
+
+def logits_fused(e, w, masked_pos, ids, scores, num_masked, k, temperature, workspace, status, rows_capacity=0, u=None, seed=0, step=0,
+                 row_offset=0, seed_dev=None, only_masked_id=None, aten=None):
+    """to_logits + top-k / gumbel argmax / confidence on the rows listed in masked_pos without a [rows, V] logits buffer."""
+    a = L.LogitsFusedArgs()
+    a.e = _chk(e).data_ptr(); a.w = _chk(w).data_ptr(); a.K = e.shape[1]; a.rows_capacity = rows_capacity
+    assert e.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[1] == e.shape[1]
+    a.workspace = workspace.data_ptr(); a.workspace_bytes = workspace.numel() * workspace.element_size(); a.status = status.data_ptr()
+    s = a.s
+    s.masked_pos = masked_pos.data_ptr(); s.ids = ids.data_ptr(); s.scores = scores.data_ptr(); s.u = L.ptr(u)
+    s.B, s.n = ids.shape; s.num_masked = num_masked; s.V = w.shape[0]; s.k = k; s.temperature = temperature
+    s.seed = seed; s.step = step; s.row_offset = row_offset; s.seed_dev = L.ptr(seed_dev)
+    if only_masked_id is not None:
+        s.only_masked = 1; s.mask_id = only_masked_id
+    if aten is not None:
+        s.rng_mode = 1; s.aten_offset = aten[0]; s.aten_offset_dev = L.ptr(aten[1]); s.aten_stride = aten[2]
+    L.call("mmg_logits_fused", a)
+
+
 def critic_score(x_cond, x_null, gamma, w, bias, cond_scale, noise_mul, scores, u=None, seed=0, step=0, row_offset=0, seed_dev=None,
                  aten=None):
     """scores[r] = CFG(dot(LN(x[r]) * gamma, w) + bias) + (u[r] - 0.5) * noise_mul   (ref: muse_maskgit_pytorch.py:590-600)"""

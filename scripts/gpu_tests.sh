@@ -21,4 +21,5 @@ runall kernels 900 tests/test_gpu_kernels.py
 runall models 900 tests/test_gpu_models.py
 runall aten_rng 600 tests/test_gpu_aten_rng.py
 runall full_config 900 tests/test_gpu_full_config.py
+runall fused_tail 600 tests/test_gpu_fused_tail.py
 cat $OUT/summary.txt

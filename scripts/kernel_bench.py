@@ -90,6 +90,24 @@ if want("sample"):
         report(f"logits_sample rows={rows} V=65536 k=6554 T=0", timeit(lambda: ops.logits_sample(lg, mp, ids, sc, nm, 6554, 0.0, seed=1)), bytes_=rows * V * 4)
         del lg
 
+if want("fused"):
+    # to_logits + sampling tail: materialised (GEMM -> [rows, V] fp32 -> sampler) vs fused (candidate lists out of the GEMM epilogue)
+    V, K, n, b, k = 65536, 512, 256, 64, 6554
+    w = (torch.randn((V, K), device="cuda") * K ** -0.5).to(bf)
+    for rows in (16384, 10240, 4096, 64):
+        nm = rows // b
+        e = torch.randn((rows, K), device="cuda").to(bf)
+        mp = torch.arange(nm, device="cuda", dtype=torch.int32).repeat(b, 1).contiguous()
+        ids = torch.full((b, n), V, device="cuda", dtype=torch.long); sc = torch.zeros((b, n), device="cuda")
+        lg = torch.empty((rows, V), device="cuda")
+        def unfused():
+            ops.linear(e, w, lg); ops.logits_sample(lg, mp, ids, sc, nm, k, 1.0, seed=1)
+        report(f"tail materialised rows={rows}: logits GEMM + logits_sample", timeit(unfused), flops=2.0 * rows * V * K)
+        ws = torch.empty((ops.logits_fused_workspace_bytes(rows, V, K, k),), dtype=torch.uint8, device="cuda"); st = torch.zeros((2,), dtype=torch.int32, device="cuda")
+        report(f"tail fused        rows={rows}: mmg_logits_fused (6 launches)", timeit(lambda: ops.logits_fused(e, w, mp, ids, sc, nm, k, 1.0, ws, st, rows_capacity=rows, seed=1)), flops=2.0 * rows * V * K)
+        print(f"    fallback rows so far {st.tolist()}", flush=True)
+        del lg, ws
+
 if want("attn"):
     for name, B, Tq, Tk, masked in [("self  B=128 h=8 Tq=256 Tk=257", 128, 256, 257, False), ("cross B=64 h=8 Tq=256 Tk=33", 64, 256, 33, True)]:
         heads = 8
