@@ -216,7 +216,7 @@ def _gemm_flops(name, a):
     if name == "mmg_conv_transpose2d":
         return 2.0 * a.B * a.H * a.W * a.Cout * 16 * a.Cin
     if name == "mmg_logits_fused":
-        return 2.0 * a.R * a.V * a.K
+        return 2.0 * a.s.B * a.s.num_masked * a.s.V * a.K
     return 0.0
 
 
@@ -240,7 +240,8 @@ def kernel_roofline(mg, texts, te_dev, pk):
         e1.record()
         rec.append((name, e0, e1, _gemm_flops(name, a)))
 
-    graph_mode = mg.use_cuda_graph
+    graph_mode, check_mode = mg.use_cuda_graph, mg.check_fused_tail
+    mg.check_fused_tail = False                                # its 4-byte host read is not capturable
     mg.transformer.encode_text = lambda t: te_dev
     kw = dict(timesteps=TIMESTEPS, cond_scale=COND_SCALE)
     how = "eager"
@@ -272,7 +273,7 @@ def kernel_roofline(mg, texts, te_dev, pk):
             torch.cuda.synchronize()
     finally:
         _lib.call = orig
-        mg.use_cuda_graph = graph_mode
+        mg.use_cuda_graph, mg.check_fused_tail = graph_mode, check_mode
     tot = {}
     for name, e0, e1, fl in rec:
         d = tot.setdefault(name, [0.0, 0.0, 0])

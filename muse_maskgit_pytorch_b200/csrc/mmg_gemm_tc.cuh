@@ -284,7 +284,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         if (c + c_step >= BN / 64) {               // last chunk is in registers: hand the accumulator stage back before the math
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) { if (PAIR) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u); else mbar_arrive(tmem_empty + acc); }
+          if (lane == 0) { if (PAIR) mbar_arrive_remote(tmem_empty0 + (uint32_t)acc * 8u); else mbar_arrive(tmem_empty + acc); }
           if (tr) MMG_TR(6, MMG_CLK());
           released = true;
         }
@@ -352,7 +352,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       if (!released) {                             // warps that own no chunk of this tile
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u); else mbar_arrive(tmem_empty + acc); }
+        if (lane == 0) { if (PAIR) mbar_arrive_remote(tmem_empty0 + (uint32_t)acc * 8u); else mbar_arrive(tmem_empty + acc); }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (LNF) {

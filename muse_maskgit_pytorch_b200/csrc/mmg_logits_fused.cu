@@ -4,7 +4,7 @@
 //   1. sample GEMM     S[r, j] = e_r . W[j * stride]      ns = min(V, 4096) evenly spaced vocabulary rows (the tcgen05 GEMM on a strided view of W)
 //   2. threshold       t_lo[r] = sample quantile whose expected exceedance count in the full row is k + 4 sigma (exact k-th value when ns == V)
 //   3. fused GEMM      the tcgen05 logits GEMM, 128 x 256 tiles, whose epilogue keeps per-row online-softmax partials (max, sum exp) in registers
-//                      and appends the candidates {x >= t_lo[r]} (12 % of the logits) to per-(row, split, half) lists: each epilogue thread owns
+//                      and appends the candidates {x >= t_lo[r]} (12 % of the logits) to per-(row, split, chunk) lists: each epilogue thread owns
 //                      one row for a whole work item (an M-tile x a contiguous range of N-tiles), compacts its candidates through a private
 //                      shared-memory FIFO and writes them as full 32-byte sectors.  The logits themselves never leave TMEM / registers.
 //   4. finish          per row: merge the partials, gather the lists (n candidates; the exact top-k is inside iff n >= k), then the same exact-rank
@@ -24,22 +24,30 @@ namespace mmg {
 int linear_impl(const mmg_linear_args* a, const int* skip_if_zero, void* stream);      // mmg_gemm.cu
 
 constexpr int LF_BM = 128, LF_BN = 256, LF_BK = 64;
-constexpr int LF_THREADS = 384, LF_EPI_WARPS = 8;
-constexpr int LF_FIFO = 16;                 // candidate entries of the per-thread shared-memory FIFO (flushed 4 at a time)
+constexpr int LF_EPI_WARPS = 8, LF_THREADS = 128 + 32 * LF_EPI_WARPS;   // warpgroup 0: TMA / MMA; 2 epilogue warpgroups
+constexpr int LF_SEGS = 2;                  // list segments per (row, split): epilogue warpgroup h owns the 64-column chunks h and h + 2 of every tile
+constexpr int LF_FIFO = 32;                 // candidate entries of the per-thread shared-memory FIFO (drained 4 at a time after every 64 columns)
 constexpr int LF_FB_CAP = 128;              // rows per step that may take the materialised fallback
 constexpr int LF_MAX_SPLITS = 64;
 constexpr int LF_A_BYTES = LF_BM * LF_BK * 2, LF_B_BYTES = LF_BN * LF_BK * 2;
 
+// What bounds this kernel (ncu, 16 384 rows, profiles/r2_fused_tail.md): with the epilogue reduced to draining TMEM the CTA-pair main loop keeps
+// the tensor pipe 98.7 % busy (607 us), with the softmax statistics 97.5 % (624 us) — the operand feed is not the limit, and keeping A resident
+// in shared memory (half the L2 -> SM traffic) changed nothing.  The candidate emission is: it is pure issue-slot cost in the epilogue warps
+// (a predicated append per logit + the sector flushes), so the FIFO is deep enough to be drained once per 64 columns by most lanes at once.
 template <bool PAIR> struct LfCfg {
-  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int STAGES = PAIR ? 4 : 3;
   static constexpr int STAGE_BYTES = LF_A_BYTES + (PAIR ? LF_B_BYTES / 2 : LF_B_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + LF_EPI_WARPS * LF_FIFO * 32 * 8;
+  static constexpr int FIFO_BYTES = LF_EPI_WARPS * LF_FIFO * 32 * 8;
+  // [<= 1 KB to align][operand ring][barriers + padding up to the next 8 KB boundary][FIFO region, 8 KB aligned like its per-warp stride]
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 8192 + FIFO_BYTES;
 };
 
 struct alignas(64) LfParams {
   CUtensorMap tma_a, tma_b;
   int64_t R;                      // rows (sampled positions of the step)
   int num_kb, num_m_tiles, num_pm, S, npt, cap;
+  int dbg;                        // MMG_LOGITS_DBG (measurement only): 1 = epilogue without the candidate lists, 2 = epilogue only drains TMEM
   const float* thr;               // [R] candidate threshold per row
   float4* parts;                  // [R][S][2]: (running max, sum of exp(x - max), candidate count as int bits, overflow flag as int bits)
   uint2* lists;                   // [R][S][2][cap]: (logit bits, vocabulary index)
@@ -58,7 +66,9 @@ tc_logits_kernel(const __grid_constant__ LfParams p) {
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint8_t* fifo_all = smem + STAGES * STAGE_BYTES + 1024;
+  // FIFO region: aligned (in the shared-memory window) to its 8 KB per-warp stride, so that a thread's slot address is base | slot << 8
+  uint8_t* fifo_all = smem + STAGES * STAGE_BYTES + 256;
+  fifo_all += (8192u - (smem_u32(fifo_all) & 8191u)) & 8191u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = p.num_pm * p.S;
@@ -152,12 +162,13 @@ tc_logits_kernel(const __grid_constant__ LfParams p) {
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    // ===================== epilogue warps: one thread = one row of the work item =====================
+    // ===================== epilogue warps: one thread = one row of the work item x every other 64-column chunk =====================
     constexpr float LOG2E = 1.4426950408889634f;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access (warp id % 4)
     const int half = (warp - 4) >> 2;             // 0: 64-column chunks 0 and 2 of a tile, 1: chunks 1 and 3
     const int r_in_tile = quarter * 32 + lane;
-    const uint32_t fifo = smem_u32(fifo_all) + (uint32_t)(warp - 4) * (LF_FIFO * 32 * 8) + (uint32_t)lane * 8u;
+    // FIFO slot s of this thread lives at fifo | s << 8 (the warp's 8 KB region is 8 KB aligned, a slot row is 32 lanes x 8 bytes)
+    const uint32_t fifo = smem_u32(fifo_all) + (uint32_t)(warp - 4) * (LF_FIFO * 256) + (uint32_t)lane * 8u;
     const uint32_t tmem_empty0 = PAIR ? mapa_shared(smem_u32(tmem_empty), 0) : 0u;
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = unit0; item < num_items; item += unit_step) {
@@ -166,23 +177,10 @@ tc_logits_kernel(const __grid_constant__ LfParams p) {
       const int64_t row = (int64_t)m_blk * LF_BM + r_in_tile;
       const bool valid = row < p.R;
       const float tlo = valid ? __ldg(p.thr + row) : FLT_MAX;            // rows past R never produce a candidate
-      uint2* seg = p.lists + ((row * p.S + sp) * 2 + half) * (int64_t)p.cap;
+      uint2* seg = p.lists + ((row * p.S + sp) * LF_SEGS + half) * (int64_t)p.cap;
       float m_run = -1e30f, s_run = 0.f;
-      int pos = 0, flushed = 0, ovf = 0;
-      auto flush = [&]() {
-        while (pos - flushed >= 4) {
-          if (flushed + 4 <= p.cap) {
-            uint32_t w[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w[2 * i]), "=r"(w[2 * i + 1]) : "r"(fifo + (uint32_t)(((flushed + i) & (LF_FIFO - 1)) * 256)));
-            st256(seg + flushed, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
-          } else {
-            ovf = 1;
-          }
-          flushed += 4;
-        }
-      };
+      uint32_t pos8 = 0;                          // appended entries << 8 (slot byte offset before wrapping)
+      int flushed = 0, ovf = 0;
       for (int j = 0; j < p.npt; ++j) {
         const int n_blk = sp * p.npt + j;
         mbar_wait(tmem_full + acc, acc_phase);
@@ -197,52 +195,69 @@ tc_logits_kernel(const __grid_constant__ LfParams p) {
           if (c + 2 >= LF_BN / 64) {               // last chunk is in registers: hand the accumulator stage back before the math
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (PAIR) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u); else mbar_arrive(tmem_empty + acc); }
+            if (lane == 0) { if (PAIR) mbar_arrive_remote(tmem_empty0 + (uint32_t)acc * 8u); else mbar_arrive(tmem_empty + acc); }
           }
+          if (p.dbg == 2) { if (v[0] == 123.456f) m_run = v[5]; continue; }
           // ---- online softmax statistics of the row ----
-          float lm = v[0];
+          float lm = fmaxf(v[0], v[1]);
 #pragma unroll
-          for (int i = 1; i < 64; ++i) lm = fmaxf(lm, v[i]);
+          for (int i = 2; i < 64; i += 2) lm = fmaxf(lm, fmaxf(v[i], v[i + 1]));
           if (lm > m_run) { s_run *= ex2_approx((m_run - lm) * LOG2E); m_run = lm; }
           const float mb = m_run * LOG2E;
           float s0 = 0.f, s1 = 0.f;
 #pragma unroll
           for (int i = 0; i < 64; i += 2) { s0 += ex2_approx(fmaf(v[i], LOG2E, -mb)); s1 += ex2_approx(fmaf(v[i + 1], LOG2E, -mb)); }
           s_run += s0 + s1;
-          // ---- candidates >= t_lo -> private FIFO -> 32-byte sectors of this thread's list segment ----
+          if (p.dbg == 1) continue;
+          // ---- candidates >= t_lo -> private FIFO (predicated, no branch) ----
           const uint32_t col0 = (uint32_t)(n_blk * LF_BN + c * 64);
+          const uint32_t pos8_before = pos8;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float x = v[g * 8 + i];
-              if (x >= tlo) {
-                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"(fifo + (uint32_t)((pos & (LF_FIFO - 1)) * 256)), "r"(__float_as_uint(x)), "r"(col0 + (uint32_t)(g * 8 + i)) : "memory");
-                ++pos;
-              }
+          for (int i = 0; i < 64; ++i) {
+            if (v[i] >= tlo) {
+              const uint32_t a = fifo | (pos8 & ((LF_FIFO - 1) << 8));
+              asm volatile("st.shared.b32 [%0], %1;\n\tst.shared.b32 [%0+4], %2;" :: "r"(a), "r"(__float_as_uint(v[i])), "r"(col0 + (uint32_t)i) : "memory");
+              pos8 += 256u;
             }
-            if (pos - flushed >= 4) flush();
+          }
+          // more than LF_FIFO - 3 candidates in 64 columns wrapped over unflushed entries (12 % are expected: never on real rows) -> fallback row
+          if (pos8 - pos8_before > (uint32_t)((LF_FIFO - 3) << 8)) ovf = 1;
+          // ---- drain whole 32-byte sectors: most lanes have one or two to write, all at the same point ----
+          while ((int)(pos8 >> 8) - flushed >= 4) {
+            if (flushed + 4 <= p.cap) {
+              const uint32_t b0 = fifo | (((uint32_t)flushed << 8) & ((LF_FIFO - 1) << 8));      // flushed % 4 == 0: the four slots do not wrap
+              uint32_t w[8];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w[2 * i]), "=r"(w[2 * i + 1]) : "r"(b0 + (uint32_t)(i * 256)));
+              st256(seg + flushed, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+            } else {
+              ovf = 1;
+            }
+            flushed += 4;
           }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       // ---- end of the work item: the last (< 4) entries as one padded sector, then the partial record ----
+      const int pos = (int)(pos8 >> 8);
       if (valid) {
         if (pos > flushed) {
           if (flushed + 4 <= p.cap) {
+            const uint32_t b0 = fifo | (((uint32_t)flushed << 8) & ((LF_FIFO - 1) << 8));
             uint32_t w[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               w[2 * i] = 0xff7fffffu; w[2 * i + 1] = 0xffffffffu;                      // (-FLT_MAX, no index) padding
               if (flushed + i < pos)
-                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w[2 * i]), "=r"(w[2 * i + 1]) : "r"(fifo + (uint32_t)(((flushed + i) & (LF_FIFO - 1)) * 256)));
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w[2 * i]), "=r"(w[2 * i + 1]) : "r"(b0 + (uint32_t)(i * 256)));
             }
             st256(seg + flushed, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
           } else {
             ovf = 1;
           }
         }
-        p.parts[(row * p.S + sp) * 2 + half] = make_float4(m_run, s_run, __int_as_float(pos), __int_as_float(ovf));
+        p.parts[(row * p.S + sp) * LF_SEGS + half] = make_float4(m_run, s_run, __int_as_float(pos), __int_as_float(ovf));
       }
     }
   }
@@ -254,23 +269,38 @@ tc_logits_kernel(const __grid_constant__ LfParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// threshold: one CTA per row over its ns sampled logits
+// threshold: one WARP per row.  Each lane keeps 1/32 of the row's ns <= 4096 sampled logits as order-preserving keys in registers and the
+// warp walks the key bits one at a time (counts by shuffle reduction, no block barrier, no shared memory): the key of sample rank
+//   rs = mu + 4 sigma + 2   (mu = ns k / V, sigma^2 = mu (1 - k / V))      ns < V:  expected exceedance count in the full row ~ k + 4 sigma V / ns
+//   rs = k                                                                  ns == V: the exact k-th largest logit
 // ---------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SMP_THREADS)
-logits_threshold_kernel(const float* __restrict__ S, int ns, int V, int k, float* __restrict__ thr, int* __restrict__ fb_count) {
-  __shared__ SampleScratch sc;
+constexpr int THR_WARPS = 8, THR_KEYS = SMP_SAMPLE / 32;
+__global__ void __launch_bounds__(THR_WARPS * 32)
+logits_threshold_kernel(const float* __restrict__ S, int ns, int V, int k, float* __restrict__ thr, int64_t R, int* __restrict__ fb_count) {
   pdl_wait(); pdl_trigger();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t r = blockIdx.x;
-  if (r == 0 && tid == 0) *fb_count = 0;             // per-step fallback counter (the previous step's fallback kernels are done: stream order)
-  uint32_t sk[SMP_SPT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *fb_count = 0;   // per-step fallback counter (the previous step's fallback kernels are done: stream order)
+  const int64_t r = (int64_t)blockIdx.x * THR_WARPS + warp;
+  if (r >= R) return;
+  uint32_t sk[THR_KEYS];
 #pragma unroll
-  for (int j = 0; j < SMP_SPT; ++j) {
-    const int i = tid + j * SMP_THREADS;
-    sk[j] = i < ns ? fkey(S[r * ns + i]) : 0u;
+  for (int j = 0; j < THR_KEYS; ++j) {
+    const int i = lane + j * 32;
+    sk[j] = i < ns ? fkey(ld_stream(S + r * ns + i)) : 0u;      // key 0 sorts below every real value
   }
-  const float tlo = sample_threshold(sk, ns, V, k, sc, warp, lane);
-  if (tid == 0) thr[r] = tlo;
+  int rs;
+  if (ns == V) rs = k < ns ? k : ns;
+  else { const float pf = (float)k / (float)V, mu = pf * ns; rs = (int)(mu + 4.0f * sqrtf(mu * (1.f - pf)) + 2.f); }
+  uint32_t prefix = 0;
+  const int last_bit = ns == V ? 0 : 12;                     // 20 key bits are plenty for a lower bound; the exact case walks all 32
+  for (int bit = 31; bit >= last_bit; --bit) {               // one bit per round: a single compare + count per key (two bits cost three)
+    const uint32_t c = prefix | (1u << bit);
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < THR_KEYS; ++j) n += (sk[j] >= c);
+    if ((int)__reduce_add_sync(0xffffffffu, n) >= rs) prefix = c;
+  }
+  if (lane == 0) thr[r] = prefix ? key_to_float(prefix) : -FLT_MAX;      // -FLT_MAX: no usable threshold, the row overflows its lists -> fallback
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -290,8 +320,8 @@ logits_finish_kernel(const mmg_logits_sample_args a, float tdiv, const LfFinish 
   float* lval = reinterpret_cast<float*>(smraw);                 // [SMP_CAP]
   int* lidx = reinterpret_cast<int*>(lval + SMP_CAP);            // [SMP_CAP]
   __shared__ SampleScratch sc;
-  __shared__ int s_off[2 * LF_MAX_SPLITS + 1];
-  __shared__ float s_m[2 * LF_MAX_SPLITS], s_s[2 * LF_MAX_SPLITS];
+  __shared__ int s_off[LF_SEGS * LF_MAX_SPLITS + 1];
+  __shared__ float s_m[LF_SEGS * LF_MAX_SPLITS], s_s[LF_SEGS * LF_MAX_SPLITS];
   __shared__ float s_max, s_sum;
   __shared__ int s_n, s_bad, s_slot;
   constexpr float LOG2E = 1.4426950408889634f;
@@ -302,7 +332,7 @@ logits_finish_kernel(const mmg_logits_sample_args a, float tdiv, const LfFinish 
   const int64_t r = blockIdx.x;
   const int b = (int)(r / a.num_masked);
   const int pos = a.masked_pos[r];
-  const int nseg = 2 * f.S;
+  const int nseg = LF_SEGS * f.S;
   if (tid == 0) { s_bad = 0; s_off[0] = 0; }
   __syncthreads();
   if (tid < nseg) {
@@ -337,11 +367,30 @@ logits_finish_kernel(const mmg_logits_sample_args a, float tdiv, const LfFinish 
         reinterpret_cast<uint4*>(f.e_fb + (int64_t)slot * f.K)[i] = reinterpret_cast<const uint4*>(f.e + r * f.K)[i];
     return;
   }
-  // gather: segment by segment, coalesced
-  for (int sgi = 0; sgi < nseg; ++sgi) {
-    const int o = s_off[sgi], c = s_off[sgi + 1] - o;
-    const uint2* src = f.lists + (r * nseg + sgi) * (int64_t)f.cap;
-    for (int i = tid; i < c; i += SMP_THREADS) { const uint2 en = src[i]; lval[o + i] = __uint_as_float(en.x); lidx[o + i] = (int)en.y; }
+  // gather: flat index -> (segment, offset) by a fixed-depth search over the <= 128 segment offsets; the (up to 18) global loads of a thread
+  // are all issued before the first one is consumed
+  {
+    constexpr int PER = (SMP_CAP + SMP_THREADS - 1) / SMP_THREADS;
+    const uint2* src[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = tid + j * SMP_THREADS;
+      int lo = 0;                                                // largest sgi with s_off[sgi] <= i
+#pragma unroll
+      for (int step = LF_SEGS * LF_MAX_SPLITS / 2; step >= 1; step >>= 1) { const int t = lo + step; if (t < nseg && s_off[t] <= i) lo = t; }
+      src[j] = f.lists + (r * nseg + lo) * (int64_t)f.cap + (i - s_off[lo]);
+    }
+    uint2 en[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      en[j] = make_uint2(0u, 0u);
+      if (tid + j * SMP_THREADS < n) asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(en[j].x), "=r"(en[j].y) : "l"(src[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = tid + j * SMP_THREADS;
+      if (i < n) { lval[i] = __uint_as_float(en[j].x); lidx[i] = (int)en[j].y; }
+    }
   }
   __syncthreads();
   int win_v; float win_x;
@@ -361,8 +410,8 @@ static inline uint64_t up256(uint64_t x) { return (x + 255) & ~uint64_t(255); }
 
 struct LfPlan { int pair, num_m_tiles, num_pm, S, npt, cap, ns, stride; };
 
-// Splits of the N range: the static schedule hands item i to unit i % units; pick the power-of-two S (npt = NT / S >= 2 tiles per item)
-// with the smallest makespan ceil(items / units) * npt, the smallest such S on ties (fewer partial records).
+// Splits of the N range: the static schedule hands item i to unit i % units; pick the smallest power-of-two S (npt = NT / S >= 2 tiles per
+// item) whose makespan ceil(items / units) * npt is within 4 % of the best one.
 static LfPlan lf_plan(int64_t R, int V, int k) {
   LfPlan pl{};
   pl.num_m_tiles = (int)((R + LF_BM - 1) / LF_BM);
@@ -370,21 +419,26 @@ static LfPlan lf_plan(int64_t R, int V, int k) {
   pl.num_pm = pl.pair ? (pl.num_m_tiles + 1) / 2 : pl.num_m_tiles;
   const int units = pl.pair ? num_sms() / 2 : num_sms();
   const int NT = V / LF_BN;
-  int best_s = 1; long best = -1;
+  long best = -1;
+  auto span_of = [&](int s) { const long items = (long)pl.num_pm * s; return ((items + units - 1) / units) * (long)(NT / s); };
   for (int s = 1; s <= LF_MAX_SPLITS && s <= NT; s *= 2) {
-    if (NT % s) break;
-    if (s > 1 && NT / s < 2) break;
-    const long items = (long)pl.num_pm * s, span = ((items + units - 1) / units) * (NT / s);
-    if (best < 0 || span < best) { best = span; best_s = s; }
+    if (NT % s || (s > 1 && NT / s < 2)) break;
+    const long span = span_of(s);
+    if (best < 0 || span < best) best = span;
+  }
+  int best_s = 1;                                              // the smallest S within 4 % of the best makespan: fewer, longer list segments
+  for (int s = 1; s <= LF_MAX_SPLITS && s <= NT; s *= 2) {
+    if (NT % s || (s > 1 && NT / s < 2)) break;
+    if (span_of(s) * 100 <= best * 104) { best_s = s; break; }
   }
   pl.S = best_s; pl.npt = NT / best_s;
   pl.stride = V > SMP_SAMPLE ? V / SMP_SAMPLE : 1;
   pl.ns = V / pl.stride;
-  // list capacity per (row, split, half): the candidates of a row (at most SMP_CAP or the row falls back anyway) spread evenly over the 2 S
+  // list capacity per (row, split, chunk): the candidates of a row (at most SMP_CAP or the row falls back anyway) spread evenly over the 4 S
   // segments, plus 6 binomial sigmas, as whole 32-byte sectors
-  const double per = (double)SMP_CAP / (2.0 * pl.S);
+  const double per = (double)SMP_CAP / ((double)LF_SEGS * pl.S);
   int cap = (int)(per + 6.0 * sqrt(per) + 8.0);
-  if (cap > LF_BN * pl.npt / 2) cap = LF_BN * pl.npt / 2;      // a segment cannot hold more than the columns it sees (128 per tile and half)
+  if (cap > 128 * pl.npt) cap = 128 * pl.npt;                  // a segment cannot hold more than the columns it sees (128 per tile)
   pl.cap = (cap + 3) / 4 * 4;
   (void)k;
   return pl;
@@ -398,7 +452,7 @@ static LfWs lf_carve(int64_t R_max, int V, int K) {
   for (int64_t R = LF_BM; ; R += LF_BM) {                       // every row count of a step up to R_max (S shrinks as R grows)
     const int64_t Rc = R < R_max ? R : R_max;
     const LfPlan pl = lf_plan(Rc, V, 1);
-    const uint64_t pb = (uint64_t)Rc * pl.S * 2 * 16, lb = (uint64_t)Rc * pl.S * 2 * pl.cap * 8;
+    const uint64_t pb = (uint64_t)Rc * pl.S * LF_SEGS * 16, lb = (uint64_t)Rc * pl.S * LF_SEGS * pl.cap * 8;
     if (pb > parts) parts = pb;
     if (lb > lists) lists = lb;
     if (R >= R_max) break;
@@ -504,12 +558,13 @@ extern "C" int mmg_logits_fused(const mmg_logits_fused_args* a, void* stream) {
     if ((rc = linear_impl(&l, nullptr, stream))) return rc;
   }
   // 2. per-row candidate threshold
-  MMG_CUDA(launch_pdl(logits_threshold_kernel, dim3((unsigned)R), dim3(SMP_THREADS), 0, st, (const float*)S, pl.ns, s.V, s.k, thr, fb_count));
+  MMG_CUDA(launch_pdl(logits_threshold_kernel, dim3((unsigned)((R + THR_WARPS - 1) / THR_WARPS)), dim3(THR_WARPS * 32), 0, st, (const float*)S, pl.ns, s.V, s.k, thr, R, fb_count));
   MMG_LAUNCHED();
   {   // 3. the logits GEMM with the candidate / softmax epilogue
     LfParams p{};
     p.R = R; p.num_kb = a->K / LF_BK; p.num_m_tiles = pl.num_m_tiles; p.num_pm = pl.num_pm; p.S = pl.S; p.npt = pl.npt; p.cap = pl.cap;
     p.thr = thr; p.parts = parts; p.lists = lists;
+    { const char* e = getenv("MMG_LOGITS_DBG"); p.dbg = e ? atoi(e) : 0; }
     uint64_t da[2] = {(uint64_t)a->K, (uint64_t)R}; uint64_t sa[1] = {(uint64_t)a->K * 2}; uint32_t ba[2] = {LF_BK, LF_BM};
     if ((rc = make_tmap_bf16(&p.tma_a, a->e, 2, da, sa, ba))) return rc;
     uint64_t db[2] = {(uint64_t)a->K, (uint64_t)s.V}; uint64_t sb[1] = {(uint64_t)a->K * 2}; uint32_t bb[2] = {LF_BK, (uint32_t)(pl.pair ? LF_BN / 2 : LF_BN)};

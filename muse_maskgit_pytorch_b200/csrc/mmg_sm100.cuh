@@ -50,6 +50,11 @@ __device__ __forceinline__ void st_cluster_v2f32(uint32_t cluster_addr, float a,
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
+// arrive on a peer CTA's barrier WITHOUT the cluster-scope release (which costs MEMBAR.ALL.GPU + ERRBAR and waits for every global store the
+// thread has in flight): for hand-offs that publish no memory, e.g. returning a TMEM accumulator stage after tcgen05.ld + tcgen05.fence
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
