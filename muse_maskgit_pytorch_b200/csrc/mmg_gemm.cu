@@ -114,10 +114,12 @@ static int launch_tc_pair(const TcGemmParams& p, cudaStream_t st) {
   return MMG_OK;
 }
 
-// CTA pairs (cta_group::2) cut the L2->SM operand traffic by a third and deepen the ring to six stages.  They win where the operand
-// feed is the limiter: long K loops (8192^3: 788 -> 732 us = 88 % of the measured cuBLAS rate; the VAE 3x3 convolutions, K = 9 Cin:
-// -10 %; FF2, K = 1408: 57 -> 51 us) and the logits GEMM (-1..5 %).  The K = 512 GEMMs with a register epilogue (QKV, GEGLU) and
-// the short residual GEMM get slower in lock-step pairs and stay on single CTAs.  MMG_GEMM_PAIR = 0 / 1 forces the choice.
+// CTA pairs (cta_group::2) cut the L2->SM operand traffic by a third and deepen the ring to six stages: 8192^3 788 -> 732 us (88 % of the
+// measured cuBLAS rate), the VAE 3x3 convolutions (K = 9 Cin) -10 %, FF2 (K = 1408) 57 -> 51 us.  Round 2: the epilogue warps used to hand
+// the TMEM stage back to the leader CTA with mbarrier.arrive.release.cluster, which compiles to MEMBAR.ALL.GPU + ERRBAR and made every
+// warp wait, once per tile, for all of its global stores; with the plain remote arrive (mbar_arrive_remote) pairs also win for the K = 512
+// GEMMs with register epilogues (QKV 54 -> 48 us, GEGLU FF1 101 -> 89 us, fp32 logits 741 -> 640 us) and are the default for every dense
+// product with 256-column tiles; the short residual GEMM (N = 512, two column tiles) stays on single CTAs.  MMG_GEMM_PAIR = 0 / 1 forces the choice.
 static bool use_pair(const TcGemmParams& p, int bn, int epi_mode) {
   static const int forced = [] { const char* e = getenv("MMG_GEMM_PAIR"); return e ? atoi(e) : -1; }();
   if (bn != 256 || forced == 0 || p.num_m_tiles < 2) return false;
@@ -125,6 +127,7 @@ static bool use_pair(const TcGemmParams& p, int bn, int epi_mode) {
   if (((p.num_m_tiles + 1) / 2) * p.num_n_tiles < 64) return false;
   if (epi_mode == 3) return true;
   if (epi_mode == 2) return p.num_kb >= 16;
+  if (p.mode == 0) return true;                                  // dense products: QKV, GEGLU, plain stores
   return p.num_kb >= 64 && p.epi.kind != MMG_EPI_CONVT && p.epi.kind != MMG_EPI_CONVT_RGB;
 }
 
