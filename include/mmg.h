@@ -133,13 +133,15 @@ typedef struct {
 } mmg_conv_transpose2d_args;
 int mmg_conv_transpose2d(const mmg_conv_transpose2d_args* a, void* stream);
 
-/* First encoder conv: 5x5, Cin = channels (3), fp32 NCHW image in, NHWC act out.  replaces vqgan_vae.py:231.     */
+/* First encoder conv: k x k (odd k <= 9, padding k / 2; the reference default is 5), Cin = channels (<= 4), fp32 NCHW image in, NHWC act
+ * out.  replaces vqgan_vae.py:231.                                                                                  */
 typedef struct {
   const float* img;        /* [B, C, H, W] fp32                                                                  */
-  const float* w;          /* [Cout, C, 5, 5] fp32 (reference layout)                                            */
+  const float* w;          /* [Cout, C, k, k] fp32 (reference layout)                                            */
   const float* bias;       /* [Cout]                                                                             */
   void*        out;        /* [B, H, W, Cout] out_dtype                                                          */
   int32_t B, C, H, W, Cout, out_dtype;
+  int32_t ksize, _pad;     /* k; 0 = 5                                                                           */
 } mmg_conv_in_args;
 int mmg_conv_in(const mmg_conv_in_args* a, void* stream);
 

@@ -3,5 +3,6 @@ lucidrains/muse-maskgit-pytorch.  Same public classes as the reference package (
 minus the trainer, which is out of scope."""
 from .vqgan_vae import VQGanVAE
 from .muse_maskgit import Transformer, MaskGit, Muse, MaskGitTransformer, TokenCritic
+from .pack_cache import set_pack_cache
 
-__all__ = ["VQGanVAE", "Transformer", "MaskGit", "Muse", "MaskGitTransformer", "TokenCritic"]
+__all__ = ["VQGanVAE", "Transformer", "MaskGit", "Muse", "MaskGitTransformer", "TokenCritic", "set_pack_cache"]

@@ -41,7 +41,7 @@ class ConvTranspose2dArgs(C.Structure):
 
 class ConvInArgs(C.Structure):
     _fields_ = [("img", vp), ("w", vp), ("bias", vp), ("out", vp), ("B", i32), ("C", i32), ("H", i32), ("W", i32),
-                ("Cout", i32), ("out_dtype", i32)]
+                ("Cout", i32), ("out_dtype", i32), ("ksize", i32), ("_pad", i32)]
 
 
 class GroupNormArgs(C.Structure):

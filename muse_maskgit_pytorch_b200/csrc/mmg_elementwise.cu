@@ -276,9 +276,10 @@ constexpr int CI_PIX = 8;
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
-               int B, int C, int H, int W, int Cout) {
+               int B, int C, int H, int W, int Cout, int ks) {
   extern __shared__ float ws[];                   // [K][Cout] then patches [CI_PIX][K]
-  const int K = C * 25;
+  const int kk = ks * ks, pad = ks / 2;
+  const int K = C * kk;
   float* patch = ws + (size_t)K * Cout;
   for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) { const int co = i / K, k = i - co * K; ws[k * Cout + co] = w[i]; }
   const int64_t pixels = (int64_t)B * H * W;
@@ -289,7 +290,7 @@ conv_in_kernel(const float* __restrict__ img, const float* __restrict__ w, const
       float v = 0.f;
       if (pix < pixels) {
         const int b = (int)(pix / ((int64_t)H * W)); const int rem = (int)(pix - (int64_t)b * H * W); const int y = rem / W, xx = rem - y * W;
-        const int c = k / 25, r = (k % 25) / 5, sx = k % 5; const int iy = y + r - 2, ix = xx + sx - 2;
+        const int c = k / kk, r = (k % kk) / ks, sx = k % ks; const int iy = y + r - pad, ix = xx + sx - pad;
         if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((int64_t)b * C + c) * H + iy) * W + ix);
       }
       patch[i] = v;
@@ -387,16 +388,18 @@ extern "C" int mmg_conv_in(const mmg_conv_in_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MMG_CHECK_ARG(a && a->img && a->w && a->out, "mmg_conv_in: NULL pointer");
   MMG_CHECK_ARG(a->C >= 1 && a->C <= 4, "mmg_conv_in: channels %d not in [1,4]", a->C);
-  const size_t smem = ((size_t)a->Cout + CI_PIX) * a->C * 25 * sizeof(float);
-  MMG_CHECK_ARG(smem <= 200 * 1024, "mmg_conv_in: Cout too large");
+  const int ks = a->ksize ? a->ksize : 5;
+  MMG_CHECK_ARG(ks >= 1 && ks <= 9 && (ks & 1), "mmg_conv_in: kernel size %d must be odd and <= 9", ks);
+  const size_t smem = ((size_t)a->Cout + CI_PIX) * a->C * ks * ks * sizeof(float);
+  MMG_CHECK_ARG(smem <= 200 * 1024, "mmg_conv_in: Cout x kernel too large for shared memory");
   int64_t pixels = ((int64_t)a->B * a->H * a->W + CI_PIX - 1) / CI_PIX;
   if (pixels > (int64_t)num_sms() * 2) pixels = (int64_t)num_sms() * 2;
   if (a->out_dtype == MMG_BF16) {
     MMG_CUDA(cudaFuncSetAttribute(conv_in_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_in_kernel<bf16><<<(unsigned)pixels, 256, smem, st>>>(a->img, a->w, a->bias, (bf16*)a->out, a->B, a->C, a->H, a->W, a->Cout);
+    conv_in_kernel<bf16><<<(unsigned)pixels, 256, smem, st>>>(a->img, a->w, a->bias, (bf16*)a->out, a->B, a->C, a->H, a->W, a->Cout, ks);
   } else {
     MMG_CUDA(cudaFuncSetAttribute(conv_in_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_in_kernel<float><<<(unsigned)pixels, 256, smem, st>>>(a->img, a->w, a->bias, (float*)a->out, a->B, a->C, a->H, a->W, a->Cout);
+    conv_in_kernel<float><<<(unsigned)pixels, 256, smem, st>>>(a->img, a->w, a->bias, (float*)a->out, a->B, a->C, a->H, a->W, a->Cout, ks);
   }
   MMG_LAUNCHED();
   return MMG_OK;

@@ -14,6 +14,7 @@
 //                      LF_FB_CAP in one step (constant logits rows ...) raises status[1]; the host then repeats the call on the materialised path.
 //
 // HBM traffic per row: ~62 KB of candidates written + read instead of 2 x 256 KB of logits; the Philox / gumbel work happens on the lists only.
+#include <cuda_fp16.h>
 #include "mmg_sm100.cuh"
 #include "mmg_tmap.cuh"
 #include "mmg_sampler.cuh"
@@ -269,12 +270,42 @@ tc_logits_kernel(const __grid_constant__ LfParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// threshold: one WARP per row.  Each lane keeps 1/32 of the row's ns <= 4096 sampled logits as order-preserving keys in registers and the
-// warp walks the key bits one at a time (counts by shuffle reduction, no block barrier, no shared memory): the key of sample rank
-//   rs = mu + 4 sigma + 2   (mu = ns k / V, sigma^2 = mu (1 - k / V))      ns < V:  expected exceedance count in the full row ~ k + 4 sigma V / ns
-//   rs = k                                                                  ns == V: the exact k-th largest logit
+// threshold: one WARP per row, no shared memory, no block barrier.
+//   ns < V (sampled rows): the lane keeps its 1/32 of the ns = 4096 sampled logits as 64 half2 registers and the warp walks the 16 bits of
+//     the order-preserving fp16 key, one bit per round: count(x >= candidate) is two packed instructions per PAIR of samples (HSET2.GE +
+//     HADD2, exact: a lane counts at most 128) and one shuffle reduction.  fp16 resolves the threshold to ~5e-4 near the 90th percentile
+//     of a logits row, i.e. to less than one sample; the threshold only has to put the sample rank at
+//       rs = mu + 4 sigma + 2   (mu = ns k / V, sigma^2 = mu (1 - k / V))  ->  expected exceedance count in the full row ~ k + 4 sigma V / ns
+//     and the exact candidate count is checked by the finishing kernel anyway.
+//   ns == V (V <= 4096): the exact k-th largest logit by the same walk over the 32 bits of the fp32 key.
 // ---------------------------------------------------------------------------------------------------------------------------
 constexpr int THR_WARPS = 8, THR_KEYS = SMP_SAMPLE / 32;
+__device__ __forceinline__ uint32_t half_key(uint32_t h) { return (h & 0x8000u) ? (~h & 0xffffu) : (h | 0x8000u); }      // fp16 bits -> monotone 16-bit key
+__device__ __forceinline__ uint32_t key_half(uint32_t k) { return (k & 0x8000u) ? (k & 0x7fffu) : (~k & 0xffffu); }      // and back
+
+__global__ void __launch_bounds__(THR_WARPS * 32)
+logits_threshold_exact_kernel(const float* __restrict__ S, int ns, int k, float* __restrict__ thr, int64_t R, int* __restrict__ fb_count) {
+  pdl_wait(); pdl_trigger();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *fb_count = 0;
+  const int64_t r = (int64_t)blockIdx.x * THR_WARPS + warp;
+  if (r >= R) return;
+  const float* row = S + r * ns;
+  uint32_t sk[THR_KEYS];
+#pragma unroll
+  for (int j = 0; j < THR_KEYS; ++j) { const int i = lane + j * 32; sk[j] = i < ns ? fkey(ld_stream(row + i)) : 0u; }
+  const int rs = k < ns ? k : ns;
+  uint32_t prefix = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t c = prefix | (1u << bit);
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < THR_KEYS; ++j) n += (sk[j] >= c);
+    if ((int)__reduce_add_sync(0xffffffffu, n) >= rs) prefix = c;
+  }
+  if (lane == 0) thr[r] = prefix ? key_to_float(prefix) : -FLT_MAX;
+}
+
 __global__ void __launch_bounds__(THR_WARPS * 32)
 logits_threshold_kernel(const float* __restrict__ S, int ns, int V, int k, float* __restrict__ thr, int64_t R, int* __restrict__ fb_count) {
   pdl_wait(); pdl_trigger();
@@ -282,25 +313,29 @@ logits_threshold_kernel(const float* __restrict__ S, int ns, int V, int k, float
   if (blockIdx.x == 0 && threadIdx.x == 0) *fb_count = 0;   // per-step fallback counter (the previous step's fallback kernels are done: stream order)
   const int64_t r = (int64_t)blockIdx.x * THR_WARPS + warp;
   if (r >= R) return;
-  uint32_t sk[THR_KEYS];
+  const float* row = S + r * ns;
+  // sampled rows: ns == SMP_SAMPLE (lf_supported), 128 samples per lane as 64 half2 (float4 loads: lane owns 4 consecutive samples per 128)
+  __half2 x2[THR_KEYS / 2];
 #pragma unroll
-  for (int j = 0; j < THR_KEYS; ++j) {
-    const int i = lane + j * 32;
-    sk[j] = i < ns ? fkey(ld_stream(S + r * ns + i)) : 0u;      // key 0 sorts below every real value
+  for (int j = 0; j < THR_KEYS / 4; ++j) {
+    const float4 v = ld_stream4(reinterpret_cast<const float4*>(row) + j * 32 + lane);
+    x2[2 * j] = __floats2half2_rn(v.x, v.y); x2[2 * j + 1] = __floats2half2_rn(v.z, v.w);
   }
-  int rs;
-  if (ns == V) rs = k < ns ? k : ns;
-  else { const float pf = (float)k / (float)V, mu = pf * ns; rs = (int)(mu + 4.0f * sqrtf(mu * (1.f - pf)) + 2.f); }
+  const float pf = (float)k / (float)V, mu = pf * ns;
+  const int rs = (int)(mu + 4.0f * sqrtf(mu * (1.f - pf)) + 2.f);
   uint32_t prefix = 0;
-  const int last_bit = ns == V ? 0 : 12;                     // 20 key bits are plenty for a lower bound; the exact case walks all 32
-  for (int bit = 31; bit >= last_bit; --bit) {               // one bit per round: a single compare + count per key (two bits cost three)
+  for (int bit = 15; bit >= 0; --bit) {
     const uint32_t c = prefix | (1u << bit);
-    int n = 0;
+    const __half t = __ushort_as_half((unsigned short)key_half(c));
+    const __half2 t2 = __half2half2(t);
+    __half2 cnt = __float2half2_rn(0.f);
 #pragma unroll
-    for (int j = 0; j < THR_KEYS; ++j) n += (sk[j] >= c);
+    for (int j = 0; j < THR_KEYS / 2; ++j) cnt = __hadd2(cnt, __hge2(x2[j], t2));          // 1.0 per sample >= t; NaN thresholds / samples count as 0
+    const int n = (int)(__low2float(cnt) + __high2float(cnt));
     if ((int)__reduce_add_sync(0xffffffffu, n) >= rs) prefix = c;
   }
-  if (lane == 0) thr[r] = prefix ? key_to_float(prefix) : -FLT_MAX;      // -FLT_MAX: no usable threshold, the row overflows its lists -> fallback
+  // prefix = the largest fp16 key with at least rs samples >= it (0: fewer than rs comparable samples -> no usable threshold)
+  if (lane == 0) thr[r] = prefix ? __half2float(__ushort_as_half((unsigned short)key_half(prefix))) : -FLT_MAX;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -367,29 +402,21 @@ logits_finish_kernel(const mmg_logits_sample_args a, float tdiv, const LfFinish 
         reinterpret_cast<uint4*>(f.e_fb + (int64_t)slot * f.K)[i] = reinterpret_cast<const uint4*>(f.e + r * f.K)[i];
     return;
   }
-  // gather: flat index -> (segment, offset) by a fixed-depth search over the <= 128 segment offsets; the (up to 18) global loads of a thread
-  // are all issued before the first one is consumed
+  // gather: warps copy whole segments (g = 16 / nseg warps share a segment when there are fewer segments than warps); a lane's loads are
+  // independent of one another, no per-entry search for the segment
   {
-    constexpr int PER = (SMP_CAP + SMP_THREADS - 1) / SMP_THREADS;
-    const uint2* src[PER];
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const int i = tid + j * SMP_THREADS;
-      int lo = 0;                                                // largest sgi with s_off[sgi] <= i
-#pragma unroll
-      for (int step = LF_SEGS * LF_MAX_SPLITS / 2; step >= 1; step >>= 1) { const int t = lo + step; if (t < nseg && s_off[t] <= i) lo = t; }
-      src[j] = f.lists + (r * nseg + lo) * (int64_t)f.cap + (i - s_off[lo]);
-    }
-    uint2 en[PER];
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      en[j] = make_uint2(0u, 0u);
-      if (tid + j * SMP_THREADS < n) asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(en[j].x), "=r"(en[j].y) : "l"(src[j]));
-    }
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const int i = tid + j * SMP_THREADS;
-      if (i < n) { lval[i] = __uint_as_float(en[j].x); lidx[i] = (int)en[j].y; }
+    constexpr int NW = SMP_THREADS / 32;
+    const int g = nseg >= NW ? 1 : NW / nseg;                    // warps per segment (nseg is a power of two times LF_SEGS = 2)
+    const int sub = warp % g, stride = 32 * g;
+    for (int sgi = warp / g; sgi < nseg; sgi += NW / g) {
+      const int o = s_off[sgi], c = s_off[sgi + 1] - o;
+      const uint2* src = f.lists + (r * nseg + sgi) * (int64_t)f.cap;
+#pragma unroll 4
+      for (int i = sub * 32 + lane; i < c; i += stride) {
+        uint2 en;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(en.x), "=r"(en.y) : "l"(src + i));
+        lval[o + i] = __uint_as_float(en.x); lidx[o + i] = (int)en.y;
+      }
     }
   }
   __syncthreads();
@@ -558,7 +585,8 @@ extern "C" int mmg_logits_fused(const mmg_logits_fused_args* a, void* stream) {
     if ((rc = linear_impl(&l, nullptr, stream))) return rc;
   }
   // 2. per-row candidate threshold
-  MMG_CUDA(launch_pdl(logits_threshold_kernel, dim3((unsigned)((R + THR_WARPS - 1) / THR_WARPS)), dim3(THR_WARPS * 32), 0, st, (const float*)S, pl.ns, s.V, s.k, thr, R, fb_count));
+  if (pl.ns == s.V) MMG_CUDA(launch_pdl(logits_threshold_exact_kernel, dim3((unsigned)((R + THR_WARPS - 1) / THR_WARPS)), dim3(THR_WARPS * 32), 0, st, (const float*)S, pl.ns, s.k, thr, R, fb_count));
+  else MMG_CUDA(launch_pdl(logits_threshold_kernel, dim3((unsigned)((R + THR_WARPS - 1) / THR_WARPS)), dim3(THR_WARPS * 32), 0, st, (const float*)S, pl.ns, s.V, s.k, thr, R, fb_count));
   MMG_LAUNCHED();
   {   // 3. the logits GEMM with the candidate / softmax epilogue
     LfParams p{};

@@ -241,6 +241,133 @@ logits_sample_kernel(const mmg_logits_sample_args a, float tdiv) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Any top-k threshold (k > SMP_CAP: topk_filter_thres below ~0.86 at V = 65536; muse_maskgit_pytorch.py:413-418 takes any value):
+// the kept set no longer fits a shared-memory list, so the row (256 KB, L2 resident after the first touch) is walked instead:
+//   1. exact k-th largest key by a bitwise descent over the whole row (32 counting passes);
+//   2. one more pass: online softmax statistics + the perturbed value of every kept element ( > k-th, plus the first k - #greater
+//      elements EQUAL to it in index order, as torch.topk keeps exactly k ) -> per-thread best -> block argmax.
+// ~35 passes over the row: a correctness path for unusual thresholds, not a fast one.
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(SMP_THREADS)
+logits_sample_bigk_kernel(const mmg_logits_sample_args a, float tdiv) {
+  __shared__ SampleScratch sc;
+  __shared__ int s_cut;
+  __shared__ float s_m, s_s;
+  pdl_wait(); pdl_trigger();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = a.V, k = a.k;
+  int64_t r = blockIdx.x;
+  const float* row = a.logits + r * (int64_t)V;
+  if (a.row_index) { if ((int)blockIdx.x >= *a.row_count_dev) return; r = a.row_index[blockIdx.x]; }
+  const int b = (int)(r / a.num_masked);
+  const int pos = a.masked_pos[r];
+  // 1. k-th largest key
+  uint32_t prefix = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = prefix | (1u << bit);
+    int c = 0;
+    for (int i = tid; i < V; i += SMP_THREADS) c += (fkey(row[i]) >= cand);
+    int tot, dummy;
+    block_sum2(c, 0, sc.red, warp, lane, tot, dummy);
+    if (tot >= k) prefix = cand;
+  }
+  int cg = 0, ce = 0;
+  for (int i = tid; i < V; i += SMP_THREADS) { const uint32_t key = fkey(row[i]); cg += (key > prefix); ce += (key == prefix); }
+  int n_gt, n_eq;
+  block_sum2(cg, ce, sc.red, warp, lane, n_gt, n_eq);
+  const int need = k - n_gt;                         // ties kept, lowest indices first (1 <= need <= n_eq)
+  // index of the last kept tie; all ties are kept in the common case (n_eq == need)
+  if (tid == 0) s_cut = V;
+  __syncthreads();
+  if (n_eq > need && warp == 0) {
+    int cnt = 0, cut = V;
+    for (int i0 = 0; i0 < V && cnt < need; i0 += 32) {
+      const int i = i0 + lane;
+      const bool tie = i < V && fkey(row[i]) == prefix;
+      const unsigned bal = __ballot_sync(0xffffffffu, tie);
+      const int c = __popc(bal);
+      if (cnt + c >= need) {                         // the need-th tie is in this group: its lane is the (need - cnt)-th set bit
+        unsigned m = bal;
+        for (int t = 0; t < need - cnt - 1; ++t) m &= m - 1;
+        cut = i0 + __ffs(m) - 1;
+      }
+      cnt += c;
+    }
+    if (lane == 0) s_cut = cut;
+  }
+  __syncthreads();
+  const int cut = s_cut;
+  // 2. statistics + perturbed argmax over the kept set
+  const int64_t grow = a.row_offset + (int64_t)b * a.n + pos;
+  const uint64_t seed = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
+  const float inv_t = 1.0f / tdiv;
+  uint64_t aq0 = 0, aoff4 = 0; uint32_t ar0 = 0;
+  if (MODE == 2) {
+    const uint64_t base = (uint64_t)grow * (uint64_t)V;
+    aq0 = base / a.aten_stride; ar0 = (uint32_t)(base - aq0 * a.aten_stride);
+    aoff4 = (a.aten_offset + (a.aten_offset_dev ? *a.aten_offset_dev : 0ull)) >> 2;
+  }
+  constexpr float LOG2E = 1.4426950408889634f;
+  float m_t = -1e30f, s_t = 0.f;
+  float bv = -FLT_MAX, bx = 0.f; int bi = 0x7fffffff;
+  for (int v = tid; v < V; v += SMP_THREADS) {
+    const float x = row[v];
+    if (x > m_t) { s_t *= ex2_approx((m_t - x) * LOG2E); m_t = x; }
+    s_t += ex2_approx((x - m_t) * LOG2E);
+    const uint32_t key = fkey(x);
+    if (key > prefix || (key == prefix && v <= cut)) {
+      float p;
+      if (MODE != 0) {
+        float u;
+        if (MODE == 1) u = a.u[((int64_t)b * a.n + pos) * V + v];
+        else { const uint32_t rr = ar0 + (uint32_t)v, dq = rr / a.aten_stride; u = aten_uniform(rr - dq * a.aten_stride, aq0 + dq, aoff4, seed); }
+        const float l1 = logf(fmaxf(u, 1e-20f));
+        p = __fdiv_rn(x, tdiv) - logf(fmaxf(-l1, 1e-20f));
+      } else {
+        const float u = (float)(philox_first((uint32_t)v, (uint32_t)a.step, (uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), (uint32_t)seed, (uint32_t)(seed >> 32)) >> 8) * (1.0f / 16777216.0f);
+        const float l1 = __logf(fmaxf(u, 1e-20f));
+        p = fmaf(x, inv_t, -__logf(fmaxf(-l1, 1e-20f)));
+      }
+      if (bi == 0x7fffffff || better(p, v, bv, bi)) { bv = p; bi = v; bx = x; }
+    }
+  }
+  // block reductions: softmax statistics, then the argmax (ties -> lowest vocabulary index)
+  {
+    float M = warp_max(m_t);
+    if (lane == 0) sc.redf[warp] = M;
+    __syncthreads();
+    M = sc.redf[lane % (SMP_THREADS / 32)];
+    M = warp_max(M);
+    float sm = warp_sum(s_t * ex2_approx((m_t - M) * LOG2E));
+    __syncthreads();
+    if (lane == 0) sc.redf[warp] = sm;
+    __syncthreads();
+    if (tid == 0) { float t = 0.f; for (int w = 0; w < SMP_THREADS / 32; ++w) t += sc.redf[w]; s_s = t; s_m = M; }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o), ox = __shfl_xor_sync(0xffffffffu, bx, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ov, oi, bv, bi))) { bv = ov; bi = oi; bx = ox; }
+  }
+  __syncthreads();
+  if (lane == 0) { sc.redf[warp] = bv; sc.redi[warp] = bi; sc.redj[warp] = __float_as_int(bx); }
+  __syncthreads();
+  if (tid == 0) {
+    bv = sc.redf[0]; bi = sc.redi[0]; bx = __int_as_float(sc.redj[0]);
+    for (int w = 1; w < SMP_THREADS / 32; ++w) {
+      const float ov = sc.redf[w]; const int oi = sc.redi[w];
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ov, oi, bv, bi))) { bv = ov; bi = oi; bx = __int_as_float(sc.redj[w]); }
+    }
+    if (bi == 0x7fffffff) { bi = 0; bx = row[0]; }                 // degenerate rows (all -inf / NaN)
+    const float pr = expf(bx - s_m) / s_s;
+    if (!a.only_masked || a.ids[(int64_t)b * a.n + pos] == a.mask_id) a.ids[(int64_t)b * a.n + pos] = bi;
+    a.scores[(int64_t)b * a.n + pos] = 1.0f - pr;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // re-mask: per batch row pick the num_masked largest scores (ties: lowest position), scatter mask_id, reset scores.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -329,7 +456,7 @@ extern "C" int mmg_logits_sample(const mmg_logits_sample_args* a, void* stream) 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MMG_CHECK_ARG(a && a->logits && a->masked_pos && a->ids && a->scores, "mmg_logits_sample: NULL pointer");
   MMG_CHECK_ARG(a->V >= 32 && a->V % 32 == 0, "mmg_logits_sample: V=%d must be a positive multiple of 32", a->V);
-  MMG_CHECK_ARG(a->k >= 1 && a->k <= a->V && a->k <= SMP_CAP, "mmg_logits_sample: k=%d out of range (<= %d)", a->k, SMP_CAP);
+  MMG_CHECK_ARG(a->k >= 1 && a->k <= a->V, "mmg_logits_sample: k=%d out of range (1 .. V=%d)", a->k, a->V);
   MMG_CHECK_ARG(!a->row_index || (a->row_count_dev && a->row_index_cap > 0), "mmg_logits_sample: row_index needs row_count_dev and row_index_cap");
   const int64_t R = a->row_index ? a->row_index_cap : (int64_t)a->B * a->num_masked;
   if (R == 0) return MMG_OK;
@@ -342,6 +469,13 @@ extern "C" int mmg_logits_sample(const mmg_logits_sample_args* a, void* stream) 
   if (attr0 != cudaSuccess || attr1 != cudaSuccess || attr2 != cudaSuccess)
     return fail(MMG_ECUDA, "cudaFuncSetAttribute(logits_sample): %s", cudaGetErrorString(attr0 != cudaSuccess ? attr0 : attr1 != cudaSuccess ? attr1 : attr2));
   float t = a->temperature; if (t < 1e-10f) t = 1e-10f;      // max(temperature, 1e-10): muse_maskgit_pytorch.py:411
+  if (a->k > SMP_CAP) {                                        // kept set larger than the candidate list: the row-walking kernel
+    if (a->u) MMG_CUDA(launch_pdl(logits_sample_bigk_kernel<1>, dim3((unsigned)R), dim3(SMP_THREADS), 0, st, *a, t));
+    else if (a->rng_mode == 1) MMG_CUDA(launch_pdl(logits_sample_bigk_kernel<2>, dim3((unsigned)R), dim3(SMP_THREADS), 0, st, *a, t));
+    else MMG_CUDA(launch_pdl(logits_sample_bigk_kernel<0>, dim3((unsigned)R), dim3(SMP_THREADS), 0, st, *a, t));
+    MMG_LAUNCHED();
+    return MMG_OK;
+  }
   if (a->u) MMG_CUDA(launch_pdl(logits_sample_kernel<1>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, *a, t));
   else if (a->rng_mode == 1) MMG_CUDA(launch_pdl(logits_sample_kernel<2>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, *a, t));
   else MMG_CUDA(launch_pdl(logits_sample_kernel<0>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, *a, t));

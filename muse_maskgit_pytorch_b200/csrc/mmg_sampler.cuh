@@ -35,6 +35,39 @@ __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint3
   return c0;
 }
 
+// The same function for many counters that differ only in c0 (one row of logits: c1 = step, c2 / c3 = global row, key = seed): the key schedule
+// and everything of rounds 1 and 2 that does not depend on c0 is computed once per row (2 of the 20 multiplies, the 20 key additions).
+struct PhiloxRow {
+  uint32_t rk0[10], rk1[10];      // round keys
+  uint32_t a, b, cx;              // round 1: n0 = a, n1 = b (constants), n2 = hi(M0 c0) ^ cx, n3 = lo(M0 c0)
+  uint32_t hi2, lo2;              // round 2: M0 * a
+};
+__device__ __forceinline__ PhiloxRow philox_row(uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  PhiloxRow r;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) { r.rk0[i] = k0; r.rk1[i] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+  r.a = (uint32_t)(p1 >> 32) ^ c1 ^ r.rk0[0]; r.b = (uint32_t)p1; r.cx = c3 ^ r.rk1[0];
+  const uint64_t p0 = (uint64_t)0xD2511F53u * r.a;
+  r.hi2 = (uint32_t)(p0 >> 32); r.lo2 = (uint32_t)p0;
+  return r;
+}
+__device__ __forceinline__ uint32_t philox_first_row(uint32_t c0, const PhiloxRow& r) {
+  // round 1
+  const uint64_t q0 = (uint64_t)0xD2511F53u * c0;
+  uint32_t n2 = (uint32_t)(q0 >> 32) ^ r.cx, n3 = (uint32_t)q0;
+  // round 2: counter (a, b, n2, n3)
+  const uint64_t q1 = (uint64_t)0xCD9E8D57u * n2;
+  uint32_t d0 = (uint32_t)(q1 >> 32) ^ r.b ^ r.rk0[1], d1 = (uint32_t)q1, d2 = r.hi2 ^ n3 ^ r.rk1[1], d3 = r.lo2;
+#pragma unroll
+  for (int i = 2; i < 10; ++i) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * d0, p1 = (uint64_t)0xCD9E8D57u * d2;
+    const uint32_t e0 = (uint32_t)(p1 >> 32) ^ d1 ^ r.rk0[i], e1 = (uint32_t)p1, e2 = (uint32_t)(p0 >> 32) ^ d3 ^ r.rk1[i], e3 = (uint32_t)p0;
+    d0 = e0; d1 = e1; d2 = e2; d3 = e3;
+  }
+  return d0;
+}
+
 // Philox4x32-10, all four output words
 __device__ __forceinline__ uint4 philox4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -154,6 +187,8 @@ __device__ __forceinline__ void sample_from_list(const mmg_logits_sample_args& a
   }
   constexpr int PER = (SMP_CAP + SMP_THREADS - 1) / SMP_THREADS;
   float pv[PER];
+  PhiloxRow prow;
+  if (MODE == 0) prow = philox_row((uint32_t)a.step, (uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
     const int s = tid + j * SMP_THREADS;
@@ -167,7 +202,7 @@ __device__ __forceinline__ void sample_from_list(const mmg_logits_sample_args& a
         const float l1 = logf(fmaxf(u, 1e-20f));
         p = __fdiv_rn(lval[s], tdiv) - logf(fmaxf(-l1, 1e-20f));
       } else {
-        const float u = (float)(philox_first((uint32_t)v, (uint32_t)a.step, (uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), (uint32_t)seed, (uint32_t)(seed >> 32)) >> 8) * (1.0f / 16777216.0f);
+        const float u = (float)(philox_first_row((uint32_t)v, prow) >> 8) * (1.0f / 16777216.0f);
         const float l1 = __logf(fmaxf(u, 1e-20f));
         p = fmaf(lval[s], inv_t, -__logf(fmaxf(-l1, 1e-20f)));
       }

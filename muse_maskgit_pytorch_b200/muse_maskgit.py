@@ -18,7 +18,7 @@ from typing import Callable, List, Optional
 import torch
 from torch import nn
 
-from . import ops, _lib
+from . import ops, _lib, pack_cache
 from .t5 import t5_encode_text, get_encoded_dim, DEFAULT_T5_NAME
 from .vqgan_vae import VQGanVAE
 
@@ -59,7 +59,9 @@ class Attention(nn.Module):
 class TransformerBlocks(nn.Module):
     def __init__(self, *, dim, depth, dim_head=64, heads=8, ff_mult=4, flash=True):
         super().__init__()
-        assert dim_head == 64, "the sm_100a attention kernels are specialised for dim_head = 64"
+        assert dim_head == 64, ("dim_head must be 64 here: the tcgen05 attention kernel (S and O tiles in TMEM, one 128-byte swizzled row per head "
+                                "vector) and the QKV epilogue are specialised for the head size every Muse config uses; the reference accepts "
+                                "any value (muse_maskgit_pytorch.py:95-110, 164-172)")
         self.dim, self.depth, self.heads, self.dim_head, self.ff_mult = dim, depth, heads, dim_head, ff_mult
         self.layers = nn.ModuleList([nn.ModuleList([Attention(dim, dim_head, heads), Attention(dim, dim_head, heads, True),
                                                     _ff_params(dim, ff_mult)]) for _ in range(depth)])
@@ -118,6 +120,13 @@ class Transformer(nn.Module):
             return self._pack
         dev = self.token_emb.weight.device
         assert dev.type == "cuda", "Transformer runs on CUDA only (libmmg.so); there is no CPU path"
+        P = pack_cache.load_or_build("transformer", self, (self.precision, self.dim_out, self.self_cond), self._build_pack, dev)
+        P["sig"] = self._weights_sig()
+        self._pack = P
+        return P
+
+    def _build_pack(self):
+        dev = self.token_emb.weight.device
         adt = self._adt()
         tb = self.transformer_blocks
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
@@ -166,8 +175,6 @@ class Transformer(nn.Module):
         P["whead"] = f32(self.to_logits.weight).reshape(-1) if self.dim_out == 1 else None     # TokenCritic head, applied in mmg_critic_score
         P["wproj"] = wa(self.text_embed_proj.weight) if isinstance(self.text_embed_proj, nn.Linear) else None
         P["sc"] = ff_pack(self.self_cond_to_init_embed) if self.self_cond else None
-        P["sig"] = self._weights_sig()
-        self._pack = P
         return P
 
     # ----- context (text / conditioning tokens): computed once per generate() ----------------------------------------

@@ -92,8 +92,10 @@ def conv_transpose2d(x, w, out, B, H, W, Cin, Cout, bias=None, rgb_w=None, rgb_b
     return out
 
 
-def conv_in(img, w, bias, out):
+def conv_in(img, w, bias, out, ksize=5):
     a = L.ConvInArgs()
+    a.ksize = ksize
+    assert tuple(w.shape[2:]) == (ksize, ksize)
     B, Cc, H, W = img.shape
     a.img = _chk(img).data_ptr(); a.w = _chk(w).data_ptr(); a.bias = L.ptr(bias); a.out = out.data_ptr()
     a.B = B; a.C = Cc; a.H = H; a.W = W; a.Cout = w.shape[0]; a.out_dtype = L.dt(out)

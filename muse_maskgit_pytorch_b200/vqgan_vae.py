@@ -13,7 +13,7 @@ from pathlib import Path
 import torch
 from torch import nn
 
-from . import ops
+from . import ops, pack_cache
 
 # conv-transpose (k4, s2, p1) parity classes: output row 2y+py reads kernel rows CT_R[py][a] at input offsets CT_D[py][a]
 CT_R = ((1, 3), (0, 2))
@@ -34,39 +34,53 @@ class _Net(nn.Module):
 
 
 class _EncDec(nn.Module):
-    """Parameter layout of the reference ResnetEncDec (vqgan_vae.py:185-232)."""
+    """Parameter layout of the reference ResnetEncDec (vqgan_vae.py:185-232): same module order, hence the same state_dict keys, for any
+    `layers`, `layer_mults`, `num_resnet_blocks` (int or per-stage tuple) and odd `first_conv_kernel_size`.  `enc_plan` / `dec_plan` list
+    what each entry of `encoders` / `decoders` is, in execution order."""
     def __init__(self, dim, channels=3, layers=4, layer_mults=None, num_resnet_blocks=1, resnet_groups=16,
                  first_conv_kernel_size=5):
         super().__init__()
-        assert dim % resnet_groups == 0
-        assert first_conv_kernel_size == 5, "only the reference default 5x5 stem is implemented"
-        self.layers, self.groups = layers, resnet_groups
+        assert dim % resnet_groups == 0, f"dimension {dim} must be divisible by {resnet_groups} (groups for the groupnorm)"
+        assert first_conv_kernel_size % 2 == 1 and 1 <= first_conv_kernel_size <= 9, \
+            "first_conv_kernel_size must be odd (the reference pads by kernel_size // 2, vqgan_vae.py:231) and at most 9 here"
+        self.layers, self.groups, self.first_k = layers, resnet_groups, first_conv_kernel_size
         mults = layer_mults if layer_mults is not None else [2 ** i for i in range(layers)]
-        assert len(mults) == layers
+        assert len(mults) == layers, "layer multipliers must be equal to designated number of layers"
         dims = [dim] + [dim * m for m in mults]
         self.dims = dims
         self.encoded_dim = dims[-1]
         if not isinstance(num_resnet_blocks, tuple):
             num_resnet_blocks = (0,) * (layers - 1) + (num_resnet_blocks,)
-        assert len(num_resnet_blocks) == layers
-        assert all(r == 0 for r in num_resnet_blocks[:-1]) and num_resnet_blocks[-1] in (0, 1), \
-            "this build implements the reference default: one res-block at the deepest stage"
-        self.has_res = num_resnet_blocks[-1] == 1
+        assert len(num_resnet_blocks) == layers, "number of resnet blocks config must be equal to number of layers"
         act = lambda: nn.LeakyReLU(0.1)
-        enc = [nn.Conv2d(channels, dim, 5, padding=2)]
-        dec = []
-        for cin, cout in zip(dims[:-1], dims[1:]):
+        enc, dec = [], []
+        for cin, cout, nres in zip(dims[:-1], dims[1:], num_resnet_blocks):
             enc.append(nn.Sequential(nn.Conv2d(cin, cout, 4, stride=2, padding=1), act()))
             dec.insert(0, nn.Sequential(nn.ConvTranspose2d(cout, cin, 4, 2, 1), act()))
-        D = dims[-1]
-        if self.has_res:
-            enc.append(_Net([nn.Conv2d(D, D, 3, padding=1), nn.GroupNorm(resnet_groups, D), act(),
-                             nn.Conv2d(D, D, 3, padding=1), nn.GroupNorm(resnet_groups, D), act(), nn.Conv2d(D, D, 1)]))
-            dec.insert(0, _Net([nn.Conv2d(D, 2 * D, 3, padding=1), nn.GLU(dim=1), nn.GroupNorm(resnet_groups, D),
-                                nn.Conv2d(D, 2 * D, 3, padding=1), nn.GLU(dim=1), nn.GroupNorm(resnet_groups, D),
-                                nn.Conv2d(D, D, 1)]))
+            for _ in range(nres):
+                enc.append(_Net([nn.Conv2d(cout, cout, 3, padding=1), nn.GroupNorm(resnet_groups, cout), act(),
+                                 nn.Conv2d(cout, cout, 3, padding=1), nn.GroupNorm(resnet_groups, cout), act(), nn.Conv2d(cout, cout, 1)]))
+                dec.insert(0, _Net([nn.Conv2d(cout, 2 * cout, 3, padding=1), nn.GLU(dim=1), nn.GroupNorm(resnet_groups, cout),
+                                    nn.Conv2d(cout, 2 * cout, 3, padding=1), nn.GLU(dim=1), nn.GroupNorm(resnet_groups, cout),
+                                    nn.Conv2d(cout, cout, 1)]))
+        enc.insert(0, nn.Conv2d(channels, dim, first_conv_kernel_size, padding=first_conv_kernel_size // 2))
         dec.append(nn.Conv2d(dim, channels, 1))
         self.encoders, self.decoders = nn.ModuleList(enc), nn.ModuleList(dec)
+
+        def plan(mods, plain):
+            out = []
+            for i, mod in enumerate(mods):
+                if isinstance(mod, _Net):
+                    out.append(("glu" if isinstance(mod.net[1], nn.GLU) else "res", i, mod.net[0].in_channels))
+                elif isinstance(mod, nn.Sequential):
+                    conv = mod[0]
+                    out.append(("up" if isinstance(conv, nn.ConvTranspose2d) else "down", i, conv.in_channels, conv.out_channels))
+                else:
+                    out.append((plain, i))          # the k x k stem of the encoder / the final 1x1 conv of the decoder
+            return out
+        self.enc_plan, self.dec_plan = plan(self.encoders, "in"), plan(self.decoders, "rgb")
+        assert self.enc_plan[0][0] == "in" and self.dec_plan[-1][0] == "rgb"
+        self.has_res = any(e[0] == "res" for e in self.enc_plan)
 
     def get_encoded_fmap_size(self, image_size):
         return image_size // (2 ** self.layers)
@@ -169,8 +183,15 @@ class VQGanVAE(nn.Module):
     def _packed(self):
         if self._pack is not None and self._pack["adt"] == self._adt():
             return self._pack
-        adt, dev = self._adt(), self.device
+        dev = self.device
         assert dev.type == "cuda", "VQGanVAE runs on CUDA only (libmmg.so); there is no CPU path"
+        P = pack_cache.load_or_build("vqgan_vae", self, (self.precision, self.lookup_free_quantization), self._build_pack, dev)
+        P["sig"] = self._weights_sig()
+        self._pack = P
+        return P
+
+    def _build_pack(self):
+        adt, dev = self._adt(), self.device
         P = {"adt": adt}
         ed, L = self.enc_dec, self.enc_dec.layers
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
@@ -184,30 +205,32 @@ class VQGanVAE(nn.Module):
             return w2d[order].contiguous(), bias[order].contiguous()
 
         P["e0_w"], P["e0_b"] = f32(ed.encoders[0].weight), f32(ed.encoders[0].bias)
-        P["enc"] = [(conv_w(ed.encoders[i][0].weight), f32(ed.encoders[i][0].bias)) for i in range(1, L + 1)]
-        if ed.has_res:
-            n = ed.encoders[L + 1].net
-            P["eres"] = dict(w1=conv_w(n[0].weight), b1=f32(n[0].bias), g1=f32(n[1].weight), be1=f32(n[1].bias),
-                             w2=conv_w(n[3].weight), b2=f32(n[3].bias), g2=f32(n[4].weight), be2=f32(n[4].bias),
-                             w3=conv_w(n[6].weight), b3=f32(n[6].bias))
-            n = ed.decoders[0].net
-            w1, b1 = glu_interleave(conv_w(n[0].weight), f32(n[0].bias))
-            w2, b2 = glu_interleave(conv_w(n[3].weight), f32(n[3].bias))
-            P["dres"] = dict(w1=w1, b1=b1, g1=f32(n[2].weight), be1=f32(n[2].bias), w2=w2, b2=b2, g2=f32(n[5].weight),
-                             be2=f32(n[5].bias), w3=conv_w(n[6].weight), b3=f32(n[6].bias))
-        off = 1 if ed.has_res else 0
-        dec = []
-        for i in range(L):
-            ct = ed.decoders[off + i][0]
-            w = ct.weight.detach().to(dev, torch.float32)                 # (Cin, Cout, 4, 4)
-            packs = []
-            for py in range(2):
-                for px in range(2):
-                    taps = [w[:, :, CT_R[py][a], CT_R[px][b]].t() for a in range(2) for b in range(2)]   # each (Cout, Cin)
-                    packs.append(torch.cat(taps, dim=1))
-            dec.append((torch.stack(packs).to(adt).contiguous(), f32(ct.bias)))
-        P["dec"] = dec
-        last = ed.decoders[off + L]
+        P["enc"], P["dec"] = {}, {}                                     # module index -> packed tensors, following enc_plan / dec_plan
+        for kind, i, *_ in ed.enc_plan:
+            if kind == "down":
+                P["enc"][i] = (conv_w(ed.encoders[i][0].weight), f32(ed.encoders[i][0].bias))
+            elif kind == "res":
+                n = ed.encoders[i].net
+                P["enc"][i] = dict(w1=conv_w(n[0].weight), b1=f32(n[0].bias), g1=f32(n[1].weight), be1=f32(n[1].bias),
+                                   w2=conv_w(n[3].weight), b2=f32(n[3].bias), g2=f32(n[4].weight), be2=f32(n[4].bias),
+                                   w3=conv_w(n[6].weight), b3=f32(n[6].bias))
+        for kind, i, *_ in ed.dec_plan:
+            if kind == "glu":
+                n = ed.decoders[i].net
+                w1, b1 = glu_interleave(conv_w(n[0].weight), f32(n[0].bias))
+                w2, b2 = glu_interleave(conv_w(n[3].weight), f32(n[3].bias))
+                P["dec"][i] = dict(w1=w1, b1=b1, g1=f32(n[2].weight), be1=f32(n[2].bias), w2=w2, b2=b2, g2=f32(n[5].weight),
+                                   be2=f32(n[5].bias), w3=conv_w(n[6].weight), b3=f32(n[6].bias))
+            elif kind == "up":
+                ct = ed.decoders[i][0]
+                w = ct.weight.detach().to(dev, torch.float32)                 # (Cin, Cout, 4, 4)
+                packs = []
+                for py in range(2):
+                    for px in range(2):
+                        taps = [w[:, :, CT_R[py][a], CT_R[px][b]].t() for a in range(2) for b in range(2)]   # each (Cout, Cin)
+                        packs.append(torch.cat(taps, dim=1))
+                P["dec"][i] = (torch.stack(packs).to(adt).contiguous(), f32(ct.bias))
+        last = ed.decoders[-1]
         P["rgb_w"], P["rgb_b"] = f32(last.weight.reshape(last.weight.shape[0], -1)), f32(last.bias)
         P["rgb_w_adt"] = P["rgb_w"].to(adt).contiguous()
         q = self.quantizer
@@ -228,8 +251,6 @@ class VQGanVAE(nn.Module):
             P["codebook"] = f32(q.embed)
             P["codebook_a"] = P["codebook"].to(adt).contiguous()
             P["code_norms"] = (P["codebook_a"].float() ** 2).sum(-1).contiguous()
-        P["sig"] = self._weights_sig()
-        self._pack = P
         return P
 
     # ----- NHWC pipelines (all arithmetic in libmmg) ---------------------------------------------------------------
@@ -240,40 +261,45 @@ class VQGanVAE(nn.Module):
         B, C, H, W = img.shape
         img = img.to(torch.float32).contiguous()
         x = torch.empty((B * H * W, ed.dims[0]), device=dev, dtype=adt)
-        ops.conv_in(img, P["e0_w"], P["e0_b"], x)
+        ops.conv_in(img, P["e0_w"], P["e0_b"], x, ksize=ed.first_k)
         h, w = H, W
-        for i, (cw, cb) in enumerate(P["enc"]):
-            cin, cout = ed.dims[i], ed.dims[i + 1]
-            y = torch.empty((B * (h // 2) * (w // 2), cout), device=dev, dtype=adt)
-            ops.conv2d(x, cw, y, B, h, w, cin, cout, kind=2, bias=cb, act=1)
-            x, h, w = y, h // 2, w // 2
-        if ed.has_res:
-            R, D = P["eres"], ed.encoded_dim
-            t1 = torch.empty_like(x); t2 = torch.empty_like(x); out = torch.empty_like(x)
-            ops.conv2d(x, R["w1"], t1, B, h, w, D, D, kind=1, bias=R["b1"])
-            ops.groupnorm_(t1, R["g1"], R["be1"], B, h * w, D, ed.groups, act=1)
-            ops.conv2d(t1, R["w2"], t2, B, h, w, D, D, kind=1, bias=R["b2"])
-            ops.groupnorm_(t2, R["g2"], R["be2"], B, h * w, D, ed.groups, act=1)
-            ops.conv2d(t2, R["w3"], out, B, h, w, D, D, kind=0, epilogue=ops.EPI_RESIDUAL, bias=R["b3"], resid=x)
-            x = out
+        for kind, i, *cc in ed.enc_plan[1:]:
+            if kind == "down":
+                cin, cout = cc
+                cw, cb = P["enc"][i]
+                y = torch.empty((B * (h // 2) * (w // 2), cout), device=dev, dtype=adt)
+                ops.conv2d(x, cw, y, B, h, w, cin, cout, kind=2, bias=cb, act=1)
+                x, h, w = y, h // 2, w // 2
+            else:                                   # ResBlock (vqgan_vae.py:267-281)
+                R, D = P["enc"][i], cc[0]
+                t1 = torch.empty_like(x); t2 = torch.empty_like(x); out = torch.empty_like(x)
+                ops.conv2d(x, R["w1"], t1, B, h, w, D, D, kind=1, bias=R["b1"])
+                ops.groupnorm_(t1, R["g1"], R["be1"], B, h * w, D, ed.groups, act=1)
+                ops.conv2d(t1, R["w2"], t2, B, h, w, D, D, kind=1, bias=R["b2"])
+                ops.groupnorm_(t2, R["g2"], R["be2"], B, h * w, D, ed.groups, act=1)
+                ops.conv2d(t2, R["w3"], out, B, h, w, D, D, kind=0, epilogue=ops.EPI_RESIDUAL, bias=R["b3"], resid=x)
+                x = out
         return x, h, w
 
     def _decode_nhwc(self, x, B, h, w):
         """fmap NHWC [B*h*w, D] -> images (B, C, H, W) fp32.  ref: vqgan_vae.py:246-249"""
         P, ed = self._packed(), self.enc_dec
-        adt, dev, L = P["adt"], x.device, self.enc_dec.layers
-        if ed.has_res:
-            R, D = P["dres"], ed.encoded_dim
-            t1 = torch.empty_like(x); t2 = torch.empty_like(x); out = torch.empty_like(x)
-            ops.conv2d(x, R["w1"], t1, B, h, w, D, 2 * D, kind=1, epilogue=ops.EPI_GLU, bias=R["b1"])
-            ops.groupnorm_(t1, R["g1"], R["be1"], B, h * w, D, ed.groups)
-            ops.conv2d(t1, R["w2"], t2, B, h, w, D, 2 * D, kind=1, epilogue=ops.EPI_GLU, bias=R["b2"])
-            ops.groupnorm_(t2, R["g2"], R["be2"], B, h * w, D, ed.groups)
-            ops.conv2d(t2, R["w3"], out, B, h, w, D, D, kind=0, epilogue=ops.EPI_RESIDUAL, bias=R["b3"], resid=x)
-            x = out
-        for i, (cw, cb) in enumerate(P["dec"]):
-            cin, cout = ed.dims[L - i], ed.dims[L - i - 1]
-            last = i == L - 1
+        adt, dev = P["adt"], x.device
+        plan = ed.dec_plan
+        for pi, (kind, i, *cc) in enumerate(plan[:-1]):
+            if kind == "glu":                       # GLUResBlock (vqgan_vae.py:251-265)
+                R, D = P["dec"][i], cc[0]
+                t1 = torch.empty_like(x); t2 = torch.empty_like(x); out = torch.empty_like(x)
+                ops.conv2d(x, R["w1"], t1, B, h, w, D, 2 * D, kind=1, epilogue=ops.EPI_GLU, bias=R["b1"])
+                ops.groupnorm_(t1, R["g1"], R["be1"], B, h * w, D, ed.groups)
+                ops.conv2d(t1, R["w2"], t2, B, h, w, D, 2 * D, kind=1, epilogue=ops.EPI_GLU, bias=R["b2"])
+                ops.groupnorm_(t2, R["g2"], R["be2"], B, h * w, D, ed.groups)
+                ops.conv2d(t2, R["w3"], out, B, h, w, D, D, kind=0, epilogue=ops.EPI_RESIDUAL, bias=R["b3"], resid=x)
+                x = out
+                continue
+            cin, cout = cc                          # ConvTranspose2d(4, 2, 1) + LeakyReLU
+            cw, cb = P["dec"][i]
+            last = pi == len(plan) - 2              # directly followed by the final 1x1 conv: fuse both (the full-resolution map stays on chip)
             fuse_rgb = last and adt == torch.bfloat16 and cout in (64, 128, 256) and cin % 64 == 0 and self._tc_tile_ok(h, w)
             if fuse_rgb:
                 img = torch.empty((B, self.channels, 2 * h, 2 * w), device=dev, dtype=torch.float32)

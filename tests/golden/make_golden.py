@@ -251,3 +251,13 @@ img = torch.from_numpy(synth.uniform("g11.img", (2, 3, 16, 16), 31))
 _, vids, _ = vae_ck.encode(img)
 save("ckpt_muse", lowres=low, superres=sup, base_ids=calls[0], superres_ids=calls[1], vae_ids=vids.long(), vae_recon=vae_ck.decode_from_ids(vids))
 print("done")
+
+# ------------------------------------------------------------------ G12: VAE with a non-default encoder / decoder layout
+# per-stage res-block counts (1, 2) and a 3x3 stem (vqgan_vae.py:185-232): the weights travel inside the fixture (default init under a seed)
+torch.manual_seed(31)
+vae_v = VQGanVAE(dim=16, layers=2, codebook_size=256, encdec_num_resnet_blocks=(1, 2), encdec_first_conv_kernel_size=3).eval()
+img = torch.from_numpy(synth.uniform("g12.img", (2, 3, 16, 16), 31))
+fq, ids, _ = vae_v.encode(img)
+sd_v = {k: v for k, v in vae_v.state_dict().items() if not k.startswith(("discr.", "_vgg."))}
+save("vae_variant", img=img, ids=ids.long(), recon=vae_v.decode_from_ids(ids), fmap=vae_v.enc_dec.encode(img),
+     **{"sd." + k: v for k, v in sd_v.items()})

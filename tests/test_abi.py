@@ -80,3 +80,17 @@ def test_baseline_ref_is_the_unmodified_reference():
     assert names and names == sorted(f for f in os.listdir(inst) if f.endswith(".py"))
     match, mismatch, errors = filecmp.cmpfiles(ref, inst, names, shallow=False)
     assert not mismatch and not errors, (mismatch, errors)
+
+
+def test_pack_cache_digest_tracks_weights():
+    """The on-disk pre-pack cache key (pack_cache.weights_digest) is a function of names, shapes, dtypes and bytes of the module's tensors."""
+    import torch
+    from muse_maskgit_pytorch_b200 import pack_cache
+    torch.manual_seed(0)
+    a, b = torch.nn.Linear(8, 4), torch.nn.Linear(8, 4)
+    b.load_state_dict(a.state_dict())
+    assert pack_cache.weights_digest(a, ("bf16",)) == pack_cache.weights_digest(b, ("bf16",))
+    assert pack_cache.weights_digest(a, ("bf16",)) != pack_cache.weights_digest(a, ("fp32",))
+    with torch.no_grad():
+        b.weight[0, 0] += 1e-3
+    assert pack_cache.weights_digest(a, ("bf16",)) != pack_cache.weights_digest(b, ("bf16",))

@@ -606,3 +606,28 @@ def test_linear_qkv_epilogue_tma_tiles(b, q_only):
         assert ok, "v: " + msg
         assert torch.equal(kk[:, :, 0].float().cpu(), nk.expand(b, -1, -1)) and torch.equal(vv[:, :, 0].float().cpu(), nv.expand(b, -1, -1))
         assert float(kk[:, :, n + 1:].abs().max()) == 0. and float(vv[:, :, n + 1:].abs().max()) == 0.
+
+
+@pytest.mark.parametrize("thres,temp", [(0.8, 1.0), (0.5, 0.3), (0.0, 1.0)])
+def test_logits_sample_any_topk_threshold(thres, temp):
+    """topk_filter_thres below ~0.86 at V = 65536 keeps more logits than the candidate list holds (k > 9216): the row-walking kernel must
+    give the reference's result (muse_maskgit_pytorch.py:413-418 accepts any threshold), including rows with many ties at the k-th value."""
+    b, n, nm, V = 1, 8, 5, 65536
+    k = O.top_k_count(V, thres)
+    assert k > 9216
+    base = torch.from_numpy(synth.normal("bigk", (nm, V), 21, 0.58))
+    base[3] = torch.round(base[3] * 4) / 4                  # few distinct values: thousands of ties at the k-th largest
+    base[4] = 0.                                            # constant row: every logit ties
+    logits = base[None]
+    u = torch.from_numpy(synth.uniform("ubigk", (b, n, V), 21))
+    g = torch.Generator().manual_seed(3)
+    mp = torch.sort(torch.randperm(n, generator=g)[:nm]).values.int()[None]
+    ids = torch.full((b, n), V, dtype=torch.long, device="cuda"); sc = torch.full((b, n), -1e5, device="cuda")
+    ops().logits_sample(dev(logits.reshape(nm, V).contiguous()), dev(mp), ids, sc, nm, k, temp, u=dev(u))
+    rows_u = torch.stack([u[0, mp[0, j]] for j in range(nm)])
+    pred, score, margin = _oracle_rows(logits.reshape(-1, V), rows_u, temp, k)
+    got = torch.stack([ids.cpu()[0, mp[0, j]] for j in range(nm)])
+    gsc = torch.stack([sc.cpu()[0, mp[0, j]] for j in range(nm)])
+    ok = margin > 1e-4
+    assert torch.equal(got[ok], pred[ok]), (got.tolist(), pred.tolist(), margin.tolist())
+    assert torch.allclose(gsc[got == pred], score[got == pred], atol=2e-6)

@@ -387,3 +387,71 @@ def test_ff_geglu_c_abi_vs_torch():
     err = (xd.cpu() - want).abs().max().item()
     assert err < 3e-2, err
     assert rel_l2(xd, want) < 5e-3
+
+
+def test_pack_cache_round_trip(tmp_path):
+    """On-disk pre-pack cache: the first model writes its packed weights, a second instance with the same checkpoint reads
+    them back (its own packing code is made to fail) and generates the same tokens; changed weights miss the cache."""
+    from muse_maskgit_pytorch_b200 import pack_cache
+    m = M()
+    pack_cache.set_pack_cache(tmp_path)
+    try:
+        before = dict(pack_cache.stats)
+        mg = make_maskgit("bf16")
+        te = util.text_embeds("g4.te", 3, 8, 128, 14).cuda()
+        mg.transformer.encode_text = lambda texts: te[:len(texts)]
+        mg.sampler_seed = 5
+        img_a, ids_a = mg.generate(["a"] * 3, timesteps=6, return_ids=True)
+        assert pack_cache.stats["stores"] >= before["stores"] + 2 and len(list(tmp_path.iterdir())) >= 2      # transformer + VAE
+        mg2 = make_maskgit("bf16")
+        boom = lambda *a, **k: (_ for _ in ()).throw(AssertionError("packing ran although the cache holds this checkpoint"))
+        mg2.transformer._build_pack = boom
+        mg2.vae._build_pack = boom
+        mg2.transformer.encode_text = lambda texts: te[:len(texts)]
+        mg2.sampler_seed = 5
+        img_b, ids_b = mg2.generate(["a"] * 3, timesteps=6, return_ids=True)
+        assert torch.equal(ids_a, ids_b) and torch.equal(img_a, img_b)
+        assert pack_cache.stats["hits"] >= before["hits"] + 2
+        with torch.no_grad():
+            mg2.transformer.to_logits.weight.mul_(1.5)
+        misses = pack_cache.stats["misses"]
+        del mg2.transformer._build_pack
+        mg2.generate(["a"] * 3, timesteps=2)
+        assert pack_cache.stats["misses"] == misses + 1
+    finally:
+        pack_cache.set_pack_cache(None)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_vae_non_default_layout_vs_reference_golden(precision):
+    """Encoder / decoder layouts other than the default (vqgan_vae.py:185-232): per-stage res-block counts (1, 2) and a 3x3 stem; the fixture
+    (made by the unmodified reference) carries its own weights, which also checks the state_dict keys of the generalised layout."""
+    g = util.golden("vae_variant")
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    vae = M().VQGanVAE(dim=16, layers=2, codebook_size=256, encdec_num_resnet_blocks=(1, 2), encdec_first_conv_kernel_size=3, precision=precision)
+    assert set(vae.state_dict()) == set(sd), set(vae.state_dict()) ^ set(sd)
+    vae.load_state_dict(sd)
+    vae = vae.cuda()
+    ids = vae.encode_ids(g["img"].cuda())
+    rec = vae.decode_from_ids(g["ids"].cuda())
+    if precision == "fp32":
+        assert torch.equal(ids.cpu(), g["ids"])
+        assert (rec.cpu() - g["recon"]).abs().max() < 1e-4
+    else:
+        assert (ids.cpu() == g["ids"]).float().mean() > 0.9
+        assert (rec.cpu() - g["recon"]).abs().max() < 5e-2
+
+
+def test_generate_accepts_any_topk_threshold():
+    """generate(topk_filter_thres=0.5) (k = 512 of 1024 here; at V = 65536 the same call keeps 32768 logits per row): runs and equals the oracle in
+    parity precision."""
+    mg = make_maskgit("fp32")
+    sd = util.transformer_sd(1024, 128, 16, 2, 2, seed=13, text_dim=128)
+    vsd = util.vae_sd(16, 2, 1024, seed=12)
+    te = util.text_embeds("g4.te", 3, 8, 128, 14)
+    mg.transformer.encode_text = lambda texts: te
+    mg.sampler_noise_fn = util.torch_noise_fn(779)
+    images, ids = mg.generate(texts=["a"] * 3, timesteps=6, topk_filter_thres=0.5, return_ids=True)
+    ref_img, ref_ids = O.generate(sd, CFG, vsd, 10, te, 4, util.torch_noise_fn(779), timesteps=6, topk_thres=0.5)
+    assert torch.equal(ids.cpu().view(3, -1), ref_ids)
+    assert (images.cpu() - ref_img).abs().max() < 1e-4
