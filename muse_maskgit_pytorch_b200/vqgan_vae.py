@@ -199,7 +199,8 @@ class VQGanVAE(nn.Module):
 
         def glu_interleave(w2d, bias):         # rows [a(32) | gate(32)] per block so the epilogue sees both halves of a unit
             C2 = w2d.shape[0]; Cc = C2 // 2
-            assert Cc % 32 == 0, "GLU fusion needs channels % 32 == 0"
+            assert Cc % 32 == 0, ("GLUResBlock channels must be a multiple of 32 here (the gate and value halves are interleaved in blocks of 32 output "
+                                  "channels for the fused conv + GLU epilogue); the reference takes any width divisible by resnet_groups (vqgan_vae.py:251-265)")
             idx = torch.arange(Cc, device=w2d.device).view(-1, 32)
             order = torch.cat((idx, idx + Cc), dim=1).reshape(-1)
             return w2d[order].contiguous(), bias[order].contiguous()

@@ -255,7 +255,7 @@ print("done")
 # ------------------------------------------------------------------ G12: VAE with a non-default encoder / decoder layout
 # per-stage res-block counts (1, 2) and a 3x3 stem (vqgan_vae.py:185-232): the weights travel inside the fixture (default init under a seed)
 torch.manual_seed(31)
-vae_v = VQGanVAE(dim=16, layers=2, codebook_size=256, encdec_num_resnet_blocks=(1, 2), encdec_first_conv_kernel_size=3).eval()
+vae_v = VQGanVAE(dim=16, layers=2, codebook_size=256, encdec_layer_mults=(2, 4), encdec_num_resnet_blocks=(1, 2), encdec_first_conv_kernel_size=3).eval()
 img = torch.from_numpy(synth.uniform("g12.img", (2, 3, 16, 16), 31))
 fq, ids, _ = vae_v.encode(img)
 sd_v = {k: v for k, v in vae_v.state_dict().items() if not k.startswith(("discr.", "_vgg."))}

@@ -424,11 +424,12 @@ def test_pack_cache_round_trip(tmp_path):
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_vae_non_default_layout_vs_reference_golden(precision):
-    """Encoder / decoder layouts other than the default (vqgan_vae.py:185-232): per-stage res-block counts (1, 2) and a 3x3 stem; the fixture
+    """Encoder / decoder layouts other than the default (vqgan_vae.py:185-232): layer_mults (2, 4), per-stage res-block counts (1, 2) and a 3x3 stem; the fixture
     (made by the unmodified reference) carries its own weights, which also checks the state_dict keys of the generalised layout."""
     g = util.golden("vae_variant")
     sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
-    vae = M().VQGanVAE(dim=16, layers=2, codebook_size=256, encdec_num_resnet_blocks=(1, 2), encdec_first_conv_kernel_size=3, precision=precision)
+    vae = M().VQGanVAE(dim=16, layers=2, codebook_size=256, encdec_layer_mults=(2, 4), encdec_num_resnet_blocks=(1, 2), encdec_first_conv_kernel_size=3,
+                       precision=precision)
     assert set(vae.state_dict()) == set(sd), set(vae.state_dict()) ^ set(sd)
     vae.load_state_dict(sd)
     vae = vae.cuda()
