@@ -42,6 +42,9 @@ int64_t     mmg_launch_count(void);
 /* Number of bf16 matrix products / convolutions of this process that fell off the tcgen05 path onto the CUDA-core kernel because of their shape
  * or alignment (K or Cin % 64, N % 64, 16-byte rows, conv tile geometry).  MMG_VERBOSE=1 logs each one to stderr. */
 int64_t     mmg_simt_fallback_count(void);
+/* Number of launches of the CUDA-core matrix-product / attention kernels (any dtype) by this process.  precision="fp32" runs its products on the
+ * tensor cores as 3-way bf16 splits (mmg_split3), so this stays 0 for a model whose shapes the TMA path takes. */
+int64_t     mmg_simt_launch_count(void);
 /* sizeof() of the argument block of entry point `name` ("mmg_linear", ...; "mmg_epilogue" for mmg_epilogue_args): lets a
  * foreign-language binding verify its struct mirror. Returns 0 for unknown names. */
 int         mmg_sizeof(const char* name);
@@ -192,7 +195,8 @@ typedef struct {
   float   scale;
   float   logit_bound;     /* optional: a guaranteed upper bound on |q.k| (for l2-normalised q, k: max_i |q_scale_i k_scale_i|);
                               > 0 lets the tensor-core kernel run a single-pass softmax against that fixed maximum. 0 = unknown. */
-  int32_t _pad;
+  int32_t split3;          /* 1 (with dtype MMG_BF16): fp32 parity on the tensor cores.  q, k, v are mmg_split3 outputs of the fp32 [.., 64] tensors
+                              (384 bf16 columns per row: q with side 0, k and v with side 1), out is fp32; exact two-pass softmax.      */
 } mmg_attention_args;
 int mmg_attention(const mmg_attention_args* a, void* stream);
 
@@ -367,6 +371,14 @@ int mmg_decode_step(const mmg_decode_step_args* a, void* stream);
 /* dtype conversion / layout helpers used by the host mirror */
 typedef struct { const void* src; void* dst; int64_t n; int32_t src_dtype, dst_dtype; } mmg_cast_args;
 int mmg_cast(const mmg_cast_args* a, void* stream);
+
+/* fp32 on the tensor cores (precision="fp32"): dst[r, 6K] bf16 = the hi / mid / lo bf16 terms of src[r, K] (hi + mid + lo == src to 24 bits),
+ * ordered per `side` (0: left operand [lo|hi|mid|mid|hi|hi], 1: right operand [hi|lo|mid|hi|mid|hi]) so that one bf16 product of the two
+ * 6K-wide operands accumulates lo*hi + hi*lo + mid*mid + mid*hi + hi*mid + hi*hi in fp32 = the fp32 product to ~2^-24.  An NHWC activation
+ * is split per pixel (rows = B*H*W, K = Cin -> 6*Cin channels), a packed conv weight per (output channel, tap).
+ * replaces: the fp32 arithmetic of nn.Linear / nn.Conv2d when parity with the fp32 reference is asked for (no reference counterpart). */
+typedef struct { const float* src; void* dst; int64_t rows, K, lds; int32_t side, _pad; } mmg_split3_args;
+int mmg_split3(const mmg_split3_args* a, void* stream);
 
 #ifdef __cplusplus
 }

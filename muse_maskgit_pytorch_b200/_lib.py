@@ -62,7 +62,7 @@ class EmbedArgs(C.Structure):
 class AttentionArgs(C.Structure):
     _fields_ = [("q", vp), ("k", vp), ("v", vp), ("out", vp), ("key_mask", vp),
                 ("B", i32), ("heads", i32), ("Tq", i32), ("Tk", i32), ("Tk_alloc", i32), ("dtype", i32),
-                ("ldo", i64), ("kv_batch_stride_zero", i32), ("scale", f32), ("logit_bound", f32), ("_pad", i32)]
+                ("ldo", i64), ("kv_batch_stride_zero", i32), ("scale", f32), ("logit_bound", f32), ("split3", i32)]
 
 
 class RemaskArgs(C.Structure):
@@ -133,16 +133,20 @@ class CastArgs(C.Structure):
     _fields_ = [("src", vp), ("dst", vp), ("n", i64), ("src_dtype", i32), ("dst_dtype", i32)]
 
 
+class Split3Args(C.Structure):
+    _fields_ = [("src", vp), ("dst", vp), ("rows", i64), ("K", i64), ("lds", i64), ("side", i32), ("_pad", i32)]
+
+
 EXPORTS = {
     "mmg_linear": LinearArgs, "mmg_conv2d": Conv2dArgs, "mmg_conv_transpose2d": ConvTranspose2dArgs,
     "mmg_conv_in": ConvInArgs, "mmg_groupnorm": GroupNormArgs, "mmg_layernorm": LayerNormArgs, "mmg_embed": EmbedArgs,
     "mmg_attention": AttentionArgs, "mmg_remask": RemaskArgs, "mmg_final_embed": FinalEmbedArgs,
     "mmg_logits_sample": LogitsSampleArgs, "mmg_vq_lfq_encode": LfqEncodeArgs, "mmg_vq_l2_argmin": L2ArgminArgs,
-    "mmg_vq_decode_codes": DecodeCodesArgs, "mmg_cast": CastArgs, "mmg_critic_score": CriticScoreArgs,
+    "mmg_vq_decode_codes": DecodeCodesArgs, "mmg_cast": CastArgs, "mmg_split3": Split3Args, "mmg_critic_score": CriticScoreArgs,
     "mmg_ff_geglu": FfGegluArgs, "mmg_decode_step": DecodeStepArgs, "mmg_logits_fused": LogitsFusedArgs,
 }
 PLAIN_EXPORTS = ("mmg_version", "mmg_last_error", "mmg_launch_count", "mmg_sizeof", "mmg_decode_step_workspace_bytes", "mmg_logits_fused_workspace_bytes",
-                 "mmg_simt_fallback_count")
+                 "mmg_simt_fallback_count", "mmg_simt_launch_count")
 
 _lib = None
 
@@ -167,6 +171,7 @@ def lib():
         l.mmg_last_error.restype = C.c_char_p
         l.mmg_launch_count.restype = C.c_int64
         l.mmg_simt_fallback_count.restype = C.c_int64
+        l.mmg_simt_launch_count.restype = C.c_int64
         l.mmg_sizeof.argtypes = [C.c_char_p]
         l.mmg_sizeof.restype = C.c_int
         l.mmg_decode_step_workspace_bytes.argtypes = [i32] * 8
@@ -191,6 +196,11 @@ def call(name, args, stream=None):
 
 def launch_count():
     return int(lib().mmg_launch_count())
+
+
+def simt_launch_count():
+    """launches of the CUDA-core GEMM / attention kernels (any dtype) so far"""
+    return int(lib().mmg_simt_launch_count())
 
 
 def simt_fallback_count():

@@ -5,6 +5,7 @@
 //     cores with S/P/O resident in TMEM.
 #include "mmg_common.cuh"
 #include "mmg_attention_tc.cuh"
+#include "mmg_attention_split.cuh"
 #include "mmg_tmap.cuh"
 #include <mutex>
 #include <float.h>
@@ -112,6 +113,30 @@ int attention_tc_launch(const mmg_attention_args* a, cudaStream_t st) {
   return attn_launch_cols<512>(p, grid, smem, st);
 }
 
+// fp32 parity on the tensor cores: q / k / v arrive as 3-way bf16 splits (384 columns per row), see mmg_attention_split.cuh
+static int attention_split_launch(const mmg_attention_args* a, cudaStream_t st) {
+  AttnSplitParams p{};
+  const int full = a->Tk / AS_KB, rem = a->Tk - full * AS_KB;
+  p.nb = rem ? full + 1 : full; p.KB_tail = rem ? (rem + 31) / 32 * 32 : AS_KB;
+  p.key_mask = a->key_mask; p.out = (float*)a->out; p.heads = a->heads; p.Tq = a->Tq; p.Tk = a->Tk; p.Tk_alloc = a->Tk_alloc;
+  p.kv_shared = a->kv_batch_stride_zero; p.ldo = a->ldo; p.scale_log2e = a->scale * 1.4426950408889634f;
+  const uint64_t BH = (uint64_t)a->B * a->heads;
+  const uint64_t kv_heads = a->kv_batch_stride_zero ? (uint64_t)a->heads : BH;
+  uint64_t str[1] = {768};
+  { uint64_t dims[2] = {384, BH * (uint64_t)a->Tq}; uint32_t box[2] = {64, 128};
+    int rc = make_tmap_bf16(&p.tma_q, a->q, 2, dims, str, box); if (rc) return rc; }
+  { uint64_t dims[2] = {384, kv_heads * (uint64_t)a->Tk_alloc}; uint32_t box[2] = {64, AS_KB};
+    int rc = make_tmap_bf16(&p.tma_k, a->k, 2, dims, str, box); if (rc) return rc;
+    rc = make_tmap_bf16(&p.tma_v, a->v, 2, dims, str, box); if (rc) return rc; }
+  static std::once_flag once; static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] { err = cudaFuncSetAttribute(attention_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM); });
+  if (err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(attention_tc_split): %s", cudaGetErrorString(err));
+  dim3 grid((a->Tq + 127) / 128, (unsigned)BH);
+  attention_tc_split_kernel<<<grid, 160, AS_SMEM, st>>>(p);
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
 }  // namespace mmg
 
 using namespace mmg;
@@ -120,6 +145,10 @@ extern "C" int mmg_attention(const mmg_attention_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MMG_CHECK_ARG(a && a->q && a->k && a->v && a->out, "mmg_attention: NULL pointer");
   MMG_CHECK_ARG(a->B > 0 && a->heads > 0 && a->Tq > 0 && a->Tk > 0 && a->Tk_alloc >= a->Tk, "mmg_attention: bad shape");
+  if (a->split3) {
+    MMG_CHECK_ARG(a->dtype == MMG_BF16 && attention_tc_supported(a) && (a->ldo % 4) == 0, "mmg_attention: split3 needs bf16 split operands, 16-byte aligned pointers, ldo %% 4");
+    return attention_split_launch(a, st);
+  }
   if (a->dtype == MMG_BF16 && attention_tc_supported(a)) return attention_tc_launch(a, st);
   dim3 grid((a->Tq + 127) / 128, a->B * a->heads);
   if (a->dtype == MMG_BF16)
@@ -128,6 +157,7 @@ extern "C" int mmg_attention(const mmg_attention_args* a, void* stream) {
   else
     attention_simt_kernel<float><<<grid, 128, 0, st>>>((const float*)a->q, (const float*)a->k, (const float*)a->v, (float*)a->out, a->key_mask,
                                                          a->heads, a->Tq, a->Tk, a->Tk_alloc, a->ldo, a->kv_batch_stride_zero, a->scale);
+  simt_launch_counter()++;
   MMG_LAUNCHED();
   return MMG_OK;
 }

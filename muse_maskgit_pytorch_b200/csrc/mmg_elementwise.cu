@@ -233,8 +233,9 @@ __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __res
   }
 }
 
-// e[j] = LNn + (LNc - LNn) * s on the masked rows; one warp per masked row; dim <= 2048.
-template <typename TE>
+// e[j] = LNn + (LNc - LNn) * s on the masked rows; one warp per masked row; dim <= 128 * NV (NV float4 per lane: the register arrays are
+// sized for the row width actually used — the one-size LN_MAXV version needed 255 registers and spilled).
+template <typename TE, int NV>
 __global__ void __launch_bounds__(256)
 final_embed_kernel(const float* __restrict__ xc, const float* __restrict__ xn, const float* __restrict__ gamma,
                    const int32_t* __restrict__ masked_pos, TE* __restrict__ e, int B, int n, int num_masked, int dim, float s) {
@@ -244,24 +245,30 @@ final_embed_kernel(const float* __restrict__ xc, const float* __restrict__ xn, c
   if (j >= (int64_t)B * num_masked) return;
   const int b = (int)(j / num_masked);
   const int64_t row = (int64_t)b * n + masked_pos[j];
-  float out[LN_MAXV * 4];
+  float out[NV * 4];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV * 4; ++i) out[i] = 0.f;
+  for (int i = 0; i < NV * 4; ++i) out[i] = 0.f;
   for (int pass = 0; pass < 2; ++pass) {
     const float* xr = (pass == 0 ? xc : xn);
     if (!xr) continue;
     xr += row * dim;
-    float v[LN_MAXV * 4]; float sum = 0.f;
+    float v[NV * 4]; float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const float t = (c + k < dim) ? xr[c + k] : 0.f; v[i * 4 + k] = t; sum += t; }
+      if (c + 3 < dim) {                 // rows are 16-byte aligned whenever dim % 4 == 0 (checked by the launcher)
+        const float4 t = *reinterpret_cast<const float4*>(xr + c);
+        v[i * 4] = t.x; v[i * 4 + 1] = t.y; v[i * 4 + 2] = t.z; v[i * 4 + 3] = t.w; sum += (t.x + t.y) + (t.z + t.w);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float t = (c + k < dim) ? xr[c + k] : 0.f; v[i * 4 + k] = t; sum += t; }
+      }
     }
     const float mean = warp_sum(sum) / (float)dim;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
 #pragma unroll
       for (int k = 0; k < 4; ++k) if (c + k < dim) { const float d = v[i * 4 + k] - mean; sq += d * d; }
@@ -269,7 +276,7 @@ final_embed_kernel(const float* __restrict__ xc, const float* __restrict__ xn, c
     const float rstd = rsqrtf(warp_sum(sq) / (float)dim + 1e-5f);
     // cond pass contributes s * LNc, null pass (1 - s) * LNn:  LNn + (LNc - LNn) * s
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
 #pragma unroll
       for (int k = 0; k < 4; ++k) if (c + k < dim) {
@@ -281,10 +288,16 @@ final_embed_kernel(const float* __restrict__ xc, const float* __restrict__ xn, c
   }
   TE* er = e + j * dim;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) if (c + k < dim) er[c + k] = from_f<TE>(out[i * 4 + k]);
+    if (c + 3 < dim) {
+      if constexpr (sizeof(TE) == 2) *reinterpret_cast<uint2*>(er + c) = make_uint2(pack_bf16(out[i * 4], out[i * 4 + 1]), pack_bf16(out[i * 4 + 2], out[i * 4 + 3]));
+      else *reinterpret_cast<float4*>(er + c) = make_float4(out[i * 4], out[i * 4 + 1], out[i * 4 + 2], out[i * 4 + 3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (c + k < dim) er[c + k] = from_f<TE>(out[i * 4 + k]);
+    }
   }
 }
 
@@ -373,6 +386,39 @@ __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = from_f<D>(to_f(s[i]));
 }
 
+// fp32 -> three bf16 terms (hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid): 24 mantissa bits in all), laid out so that ONE
+// bf16 tensor-core product over 6K columns accumulates the six significant cross terms of the fp32 product in fp32, smallest first:
+//   A side [lo | hi | mid | mid | hi | hi ]  x  W side [hi | lo | mid | hi | mid | hi]  =  lo*hi + hi*lo + mid*mid + mid*hi + hi*mid + hi*hi
+// (the dropped mid*lo, lo*mid, lo*lo terms are below 2^-24 of the product).  precision="fp32" runs its matrix products through this.
+__global__ void split3_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t rows, int64_t K, int64_t lds, int side) {
+  const int64_t kv = K >> 3;                       // 8 columns per thread
+  const int64_t total = rows * kv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / kv, c = (i - r * kv) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(src + r * lds + c), b = *reinterpret_cast<const float4*>(src + r * lds + c + 4);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t hi[4], mid[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float h[2], m[2], l[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float v = x[2 * j + e];
+        h[e] = __bfloat162float(__float2bfloat16_rn(v));
+        const float r1 = v - h[e];                                   // exact
+        m[e] = __bfloat162float(__float2bfloat16_rn(r1));
+        l[e] = r1 - m[e];                                            // exact; rounded to bf16 by the pack below
+      }
+      hi[j] = pack_bf16(h[0], h[1]); mid[j] = pack_bf16(m[0], m[1]); lo[j] = pack_bf16(l[0], l[1]);
+    }
+    const uint4 H = make_uint4(hi[0], hi[1], hi[2], hi[3]), M = make_uint4(mid[0], mid[1], mid[2], mid[3]), L = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    bf16* d = dst + r * 6 * K + c;
+    const uint4 t0 = side ? H : L, t1 = side ? L : H, t3 = side ? H : M, t4 = side ? M : H;
+    *reinterpret_cast<uint4*>(d) = t0; *reinterpret_cast<uint4*>(d + K) = t1; *reinterpret_cast<uint4*>(d + 2 * K) = M;
+    *reinterpret_cast<uint4*>(d + 3 * K) = t3; *reinterpret_cast<uint4*>(d + 4 * K) = t4; *reinterpret_cast<uint4*>(d + 5 * K) = H;
+  }
+}
+
 }  // namespace mmg
 
 using namespace mmg;
@@ -434,8 +480,13 @@ extern "C" int mmg_final_embed(const mmg_final_embed_args* a, void* stream) {
   const int64_t R = (int64_t)a->B * a->num_masked;
   if (R == 0) return MMG_OK;
   const unsigned grid = (unsigned)((R + 7) / 8);
-  if (a->e_dtype == MMG_BF16) MMG_CUDA(launch_pdl(final_embed_kernel<bf16>, dim3(grid), dim3(256), 0, st, a->x_cond, a->x_null, a->gamma, a->masked_pos, (bf16*)a->e, a->B, a->n, a->num_masked, a->dim, a->cond_scale));
-  else MMG_CUDA(launch_pdl(final_embed_kernel<float>, dim3(grid), dim3(256), 0, st, a->x_cond, a->x_null, a->gamma, a->masked_pos, (float*)a->e, a->B, a->n, a->num_masked, a->dim, a->cond_scale));
+  MMG_CHECK_ARG(a->dim % 4 == 0 && (reinterpret_cast<uintptr_t>(a->x_cond) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->x_null) & 15) == 0, "mmg_final_embed: dim %% 4, 16-byte aligned rows");
+  MMG_CHECK_ARG((reinterpret_cast<uintptr_t>(a->e) & 15) == 0, "mmg_final_embed: e must be 16-byte aligned");
+#define MMG_FE(TE, NV) MMG_CUDA(launch_pdl(final_embed_kernel<TE, NV>, dim3(grid), dim3(256), 0, st, a->x_cond, a->x_null, a->gamma, a->masked_pos, (TE*)a->e, a->B, a->n, a->num_masked, a->dim, a->cond_scale))
+  const int nv = a->dim <= 128 ? 1 : a->dim <= 256 ? 2 : a->dim <= 512 ? 4 : a->dim <= 1024 ? 8 : LN_MAXV;
+  if (a->e_dtype == MMG_BF16) { switch (nv) { case 1: MMG_FE(bf16, 1); break; case 2: MMG_FE(bf16, 2); break; case 4: MMG_FE(bf16, 4); break; case 8: MMG_FE(bf16, 8); break; default: MMG_FE(bf16, LN_MAXV); } }
+  else { switch (nv) { case 1: MMG_FE(float, 1); break; case 2: MMG_FE(float, 2); break; case 4: MMG_FE(float, 4); break; case 8: MMG_FE(float, 8); break; default: MMG_FE(float, LN_MAXV); } }
+#undef MMG_FE
   MMG_LAUNCHED();
   return MMG_OK;
 }
@@ -480,6 +531,20 @@ extern "C" int mmg_cast(const mmg_cast_args* a, void* stream) {
   if (a->src_dtype == MMG_F32 && a->dst_dtype == MMG_BF16) cast_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)a->src, (bf16*)a->dst, a->n);
   else if (a->src_dtype == MMG_BF16 && a->dst_dtype == MMG_F32) cast_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)a->src, (float*)a->dst, a->n);
   else return fail(MMG_EINVAL, "mmg_cast: unsupported dtype pair");
+  MMG_LAUNCHED();
+  return MMG_OK;
+}
+
+extern "C" int mmg_split3(const mmg_split3_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MMG_CHECK_ARG(a && a->src && a->dst, "mmg_split3: NULL pointer");
+  MMG_CHECK_ARG(a->rows >= 0 && a->K > 0 && a->K % 8 == 0 && a->lds >= a->K && a->lds % 4 == 0, "mmg_split3: K %% 8, lds %% 4 (rows %lld, K %lld, lds %lld)",
+                (long long)a->rows, (long long)a->K, (long long)a->lds);
+  MMG_CHECK_ARG((reinterpret_cast<uintptr_t>(a->src) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->dst) & 15) == 0, "mmg_split3: 16-byte alignment");
+  if (a->rows == 0) return MMG_OK;
+  const int64_t work = a->rows * (a->K / 8);
+  const unsigned grid = (unsigned)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
+  split3_kernel<<<grid, 256, 0, st>>>(a->src, reinterpret_cast<bf16*>(a->dst), a->rows, a->K, a->lds, a->side);
   MMG_LAUNCHED();
   return MMG_OK;
 }

@@ -88,6 +88,17 @@ struct Epilogue {
     }
   }
 
+  // GEGLU of one 64-column accumulator chunk [x(32) | gate(32)] -> 32 outputs (+ the row statistics of the folded LayerNorm)
+  template <bool FAST>
+  __device__ __forceinline__ void geglu_chunk(const float (&v)[64], float (&o)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = v[32 + i] * (FAST ? gelu_fast(v[i]) : gelu_erf(v[i]));
+    if (p.row_stats) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { st_a += o[i]; st_b = fmaf(o[i], o[i], st_b); }
+    }
+  }
+
   template <bool FAST>
   __device__ __forceinline__ void apply(int64_t row, int col0, float (&v)[64], int nvalid) {
     const bool bf = (p.out_dtype == MMG_BF16);
@@ -174,12 +185,7 @@ struct Epilogue {
       case MMG_EPI_GLU: {
         float o[32];
         if (kind == MMG_EPI_GEGLU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = v[32 + i] * (FAST ? gelu_fast(v[i]) : gelu_erf(v[i]));
-          if (p.row_stats) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { st_a += o[i]; st_b = fmaf(o[i], o[i], st_b); }
-          }
+          geglu_chunk<FAST>(v, o);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {

@@ -50,16 +50,16 @@ static int launch_tc_tstore(const TcGemmParams& p, cudaStream_t st) {
   return MMG_OK;
 }
 
-// QKV epilogue through per-warp tiles + TMA stores
-template <int BN>
+// QKV (MODE 4) / GEGLU (MODE 5) epilogues through per-warp tiles + TMA stores
+template <int BN, int MODE = 4>
 static int launch_tc_qkvt(const TcGemmParams& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES_RED); });
-  if (attr_err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(tc_gemm_qkvt<%d>): %s", BN, cudaGetErrorString(attr_err));
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, false, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES_RED); });
+  if (attr_err != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(tc_gemm_tiles<%d, %d>): %s", BN, MODE, cudaGetErrorString(attr_err));
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  MMG_CUDA(launch_pdl(tc_gemm_kernel<BN, false, false, 4>, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES_RED, st, p));
+  MMG_CUDA(launch_pdl(tc_gemm_kernel<BN, false, false, MODE>, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES_RED, st, p));
   MMG_LAUNCHED();
   return MMG_OK;
 }
@@ -154,8 +154,11 @@ static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_
   static const int qkvt_forced = [] { const char* ev = getenv("MMG_GEMM_QKVT"); return ev ? atoi(ev) : -1; }();
   const bool qkv_tiles = p.epi.kind == MMG_EPI_QKV && e.out_dtype == MMG_BF16 && p.mode == 0 && e.tokens % 32 == 0 && p.M % 128 == 0 && (bn == 128 || bn == 256) &&
                          (!e.nq_heads || aligned16(e.q_out)) && (!e.nk_heads || (aligned16(e.k_out) && aligned16(e.v_out))) && e.nk_heads == e.nv_heads;
-  const int epi_mode = (in_place && red_forced != 0) ? 2 : (plain_f32 && tstore_forced != 0 && bn == 256) ? 3 : (qkv_tiles && qkvt_forced != 0) ? 4 : 0;
-  const bool pair = use_pair(p, bn, epi_mode == 4 ? 0 : epi_mode);
+  static const int geglut_forced = [] { const char* ev = getenv("MMG_GEMM_GEGLUT"); return ev ? atoi(ev) : -1; }();
+  const bool geglu_tiles = p.epi.kind == MMG_EPI_GEGLU && e.out_dtype == MMG_BF16 && p.mode == 0 && bn == 256 && (e.ldo % 8) == 0 && aligned16(e.out);
+  const int epi_mode = (in_place && red_forced != 0) ? 2 : (plain_f32 && tstore_forced != 0 && bn == 256) ? 3 : (qkv_tiles && qkvt_forced != 0) ? 4 :
+                       (geglu_tiles && geglut_forced != 0) ? 5 : 0;
+  const bool pair = use_pair(p, bn, epi_mode >= 4 ? 0 : epi_mode);
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; uint64_t str[1] = {(uint64_t)ldw * 2}; uint32_t box[2] = {TC_BK, (uint32_t)(pair ? bn / 2 : bn)};
   int rc = make_tmap_bf16(&p.tma_b, w, 2, dims, str, box); if (rc) return rc;
   if (epi_mode == 4) {
@@ -169,6 +172,11 @@ static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_
     }
     if (!pair) return bn == 256 ? launch_tc_qkvt<256>(p, st) : launch_tc_qkvt<128>(p, st);
     return launch_tc_pair<256, 4>(p, st);
+  }
+  if (epi_mode == 5) {
+    uint64_t od[2] = {(uint64_t)(p.N / 2), (uint64_t)p.M}; uint64_t os[1] = {(uint64_t)e.ldo * 2}; uint32_t ob[2] = {64, 32};
+    rc = make_tmap_bf16(&p.tma_out, e.out, 2, od, os, ob); if (rc) return rc;
+    return pair ? launch_tc_pair<256, 5>(p, st) : launch_tc_qkvt<256, 5>(p, st);
   }
   if (epi_mode) {
     uint64_t od[2] = {(uint64_t)p.N, (uint64_t)p.M}; uint64_t os[1] = {(uint64_t)e.ldo * 4}; uint32_t ob[2] = {32, 32};
@@ -271,6 +279,7 @@ static int launch_simt(int dtype, const void* a, const void* w, int64_t M, int64
   MMG_CHECK_ARG(grid.y < 65536, "N too large for the fp32 path");
   if (dtype == MMG_F32) simt_gemm_kernel<float, CONV><<<grid, 256, 0, st>>>((const float*)a, (const float*)w, M, N, K, lda, ldw, g, epi);
   else simt_gemm_kernel<bf16, CONV><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)w, M, N, K, lda, ldw, g, epi);
+  simt_launch_counter()++;
   MMG_LAUNCHED();
   return MMG_OK;
 }
@@ -427,6 +436,11 @@ extern "C" int mmg_conv_transpose2d(const mmg_conv_transpose2d_args* a, void* st
 }
 
 #ifdef MMG_GEMM_TRACE
+extern "C" int mmg_trace_clear(void) {
+  void* p = nullptr;
+  if (cudaGetSymbolAddress(&p, mmg::g_gemm_trace) != cudaSuccess) return -1;
+  return (int)cudaMemset(p, 0, sizeof(mmg::g_gemm_trace));
+}
 extern "C" int mmg_trace_read(void* dst, size_t bytes) {
   return (int)cudaMemcpyFromSymbol(dst, mmg::g_gemm_trace, bytes < sizeof(mmg::g_gemm_trace) ? bytes : sizeof(mmg::g_gemm_trace));
 }

@@ -29,7 +29,7 @@ constexpr int TC_MAX_TAPS = 16;
 struct alignas(64) TcGemmParams {
   CUtensorMap tma_a[4];
   CUtensorMap tma_b;
-  CUtensorMap tma_out;      // EPI_MODE 2 / 3: the fp32 output [M, N] in boxes of 32 rows x 32 columns (128 B), SWIZZLE_128B
+  CUtensorMap tma_out;      // EPI_MODE 2 / 3: the fp32 output [M, N] in boxes of 32 rows x 32 columns (128 B), SWIZZLE_128B; EPI_MODE 5: bf16 [M, N/2], 32 x 64
   CUtensorMap tma_qkv[3];   // EPI_MODE 4: q / k / v as [rows, 64] bf16 matrices in boxes of 32 rows x 64 columns (128 B)
   int64_t M, N;
   int num_kb, num_m_tiles, num_n_tiles;
@@ -87,6 +87,9 @@ template <int BN> struct TcCfg {
 // EPI_MODE 3: plain fp32 outputs (no bias / activation; the logits GEMM) leave through the same tiles with a TMA store.
 // EPI_MODE 4: the QKV epilogue (bf16; tokens % 32 == 0 and M % 128 == 0, so a warp's 32 rows are 32 consecutive tokens of one
 // sequence and land on 32 consecutive rows of one head of q / k / v): head chunk -> tile -> one TMA store per warp and chunk.
+// EPI_MODE 5: the GEGLU epilogue (bf16 out, BN == 256): the two warps of a lane quarter take ADJACENT chunk pairs (0,1 | 2,3), so a
+// warp's 2 x 32 outputs per row are 128 contiguous bytes -> one 32-row x 128-byte tile -> one TMA store per warp and tile instead of
+// 8 row-strided 32-byte global stores per thread (which the L1 retires at 16.7 B/clk/SM, see above).
 template <int BN, bool LNF = false, bool PAIR = false, int EPI_MODE = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
@@ -94,6 +97,8 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   using Cfg = TcCfg<BN>;
   constexpr bool RED = EPI_MODE == 2 || EPI_MODE == 3, RED_ADD = EPI_MODE == 2;   // 3: same tiles, plain TMA store
   constexpr bool QKVT = EPI_MODE == 4;
+  constexpr bool GEGLUT = EPI_MODE == 5;
+  static_assert(!GEGLUT || BN == 256, "the GEGLU tile epilogue pairs adjacent 64-column chunks of a 256-column tile");
   static_assert(!(LNF && PAIR), "LayerNorm fusion and CTA pairs both claim the cluster");
   static_assert(!(LNF && EPI_MODE != 0), "the LayerNorm-fused kernel has no room for the epilogue tiles");
   constexpr int STAGES = PAIR ? Cfg::PAIR_STAGES : Cfg::STAGES;
@@ -262,7 +267,8 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         row = ((int64_t)b * p.Ho + (yt * p.TH + ty)) * p.Wo + xt * p.TW + tx;
       }
       const bool mine = !whole_row || half == 0;
-      const int c_first = whole_row ? 0 : half, c_step = whole_row ? 1 : 2;
+      const int c_first = GEGLUT ? 2 * half : whole_row ? 0 : half, c_step = (GEGLUT || whole_row) ? 1 : 2;
+      const int c_end = GEGLUT ? c_first + 2 : BN / 64;
       const bool pre = !RED && prefetch_resid && valid && mine && (n_blk * BN + c_first * 64 < p.N) && c_first < BN / 64;
       float rbuf[64];
       float ln_sum = 0.f, ln_sq = 0.f;
@@ -275,13 +281,13 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       if (valid && mine) epi.begin_row(row);
       bool released = false;
 #pragma unroll 1
-      for (int c = c_first; c < BN / 64; c += c_step) {
+      for (int c = c_first; c < c_end; c += c_step) {
         if (!mine) break;
         float v[64];
         tmem_ld_32x32b_x32(t_row + c * 64, v);
         tmem_ld_32x32b_x32(t_row + c * 64 + 32, v + 32);
         tmem_ld_wait();
-        if (c + c_step >= BN / 64) {               // last chunk is in registers: hand the accumulator stage back before the math
+        if (c + c_step >= c_end) {                 // last chunk is in registers: hand the accumulator stage back before the math
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { if (PAIR) mbar_arrive_remote(tmem_empty0 + (uint32_t)acc * 8u); else mbar_arrive(tmem_empty + acc); }
@@ -289,7 +295,24 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
           released = true;
         }
         const int col0 = n_blk * BN + c * 64;
-        if (QKVT && col0 < p.N) {
+        if (GEGLUT) {
+          // columns past N are zero accumulators (TMA zero-fills the missing W rows) and are clipped by the tensor map, rows past M too
+          float o[32];
+          epi.template geglu_chunk<true>(v, o);
+          const uint32_t wtile = smem_u32(smem + STAGES * STAGE_BYTES + 1024) + (uint32_t)(warp - 4) * 4096u;
+          const int cc = c - c_first;                       // 0 / 1: left / right 64 bytes of the warp's 128-byte rows
+          if (cc == 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }     // this warp's previous store has left the tile
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(wtile + (uint32_t)lane * 128u + (uint32_t)(((cc * 4 + j) ^ (lane & 7)) * 16)),
+                         "r"(pack_bf16(o[8 * j], o[8 * j + 1])), "r"(pack_bf16(o[8 * j + 2], o[8 * j + 3])),
+                         "r"(pack_bf16(o[8 * j + 4], o[8 * j + 5])), "r"(pack_bf16(o[8 * j + 6], o[8 * j + 7])) : "memory");
+          if (cc == 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&p.tma_out, wtile, (n_blk * BN + c_first * 64) >> 1, m_blk * TC_BM + quarter * 32); bulk_commit(); }
+          }
+        } else if (QKVT && col0 < p.N) {
           int h;
           const int which = epi.template qkv_chunk<true>(col0, v, h);
           const uint32_t wtile = smem_u32(smem + STAGES * STAGE_BYTES + 1024) + (uint32_t)(warp - 4) * 4096u;
@@ -392,7 +415,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     }
   }
 
-  if ((RED || QKVT) && warp >= 4 && lane == 0) bulk_wait0();   // every pushed tile has landed before the CTA (and its shared memory) goes away
+  if ((RED || QKVT || GEGLUT) && warp >= 4 && lane == 0) bulk_wait0();   // every pushed tile has landed before the CTA (and its shared memory) goes away
   tc_fence_before();
   __syncthreads();
   if (LNF || PAIR) cluster_sync_all();          // no CTA may exit while its peer can still write its shared memory / read its operands

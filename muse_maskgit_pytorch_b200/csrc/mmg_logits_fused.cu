@@ -348,17 +348,24 @@ struct LfFinish {
   int* status;                                // [0] += fallback rows, [1] = 1 when more rows than fb_cap needed the fallback
 };
 
+// Finisher.  One CTA per row.  The row's candidate segments (~62 KB, interleaved (logit, index) pairs) come into shared memory as ONE bulk
+// copy per segment (cp.async.bulk -> mbarrier: no registers, no per-thread round trips; the first version's per-lane 8-byte loads kept 16 KB
+// in flight per CTA and ran at 0.86 TB/s, 15 % of a generate()); the selection keeps no per-candidate registers (sample_from_pairs), so two
+// CTAs share an SM and one row's copy overlaps the other's Philox / gumbel pass.  Segments are placed at even entry offsets (16-byte aligned
+// destinations); an odd segment drags one foreign entry along, which is overwritten with padding.
 template <int MODE>
-__global__ void __launch_bounds__(SMP_THREADS)
+__global__ void __launch_bounds__(SMP_THREADS, 2)
 logits_finish_kernel(const mmg_logits_sample_args a, float tdiv, const LfFinish f) {
-  extern __shared__ uint8_t smraw[];
-  float* lval = reinterpret_cast<float*>(smraw);                 // [SMP_CAP]
-  int* lidx = reinterpret_cast<int*>(lval + SMP_CAP);            // [SMP_CAP]
+  using namespace sm100;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  uint2* lst = reinterpret_cast<uint2*>(smraw);                  // [SMP_CAP + 2 * segments]
   __shared__ SampleScratch sc;
-  __shared__ int s_off[LF_SEGS * LF_MAX_SPLITS + 1];
+  __shared__ int s_off[LF_SEGS * LF_MAX_SPLITS + 1], s_cnt[LF_SEGS * LF_MAX_SPLITS];
   __shared__ float s_m[LF_SEGS * LF_MAX_SPLITS], s_s[LF_SEGS * LF_MAX_SPLITS];
   __shared__ float s_max, s_sum;
-  __shared__ int s_n, s_bad, s_slot;
+  __shared__ int s_n, s_npad, s_bad, s_slot;
+  __shared__ int s_excl[SMP_MAX_EXCL];
+  __shared__ __align__(8) uint64_t s_bar;
   constexpr float LOG2E = 1.4426950408889634f;
 
   pdl_wait(); pdl_trigger();
@@ -368,66 +375,75 @@ logits_finish_kernel(const mmg_logits_sample_args a, float tdiv, const LfFinish 
   const int b = (int)(r / a.num_masked);
   const int pos = a.masked_pos[r];
   const int nseg = LF_SEGS * f.S;
-  if (tid == 0) { s_bad = 0; s_off[0] = 0; }
+  if (tid == 0) { s_bad = 0; mbar_init(&s_bar, 1); fence_barrier_init(); }
   __syncthreads();
   if (tid < nseg) {
     const float4 pt = f.parts[r * nseg + tid];
-    s_m[tid] = pt.x; s_s[tid] = pt.y; s_off[tid + 1] = __float_as_int(pt.z);
-    if (__float_as_int(pt.w)) s_bad = 1;
+    s_m[tid] = pt.x; s_s[tid] = pt.y; s_cnt[tid] = __float_as_int(pt.z);
+    if (__float_as_int(pt.w) || __float_as_int(pt.z) > f.cap) s_bad = 1;
   }
   __syncthreads();
-  if (tid == 0) {
-    float M = s_m[0];
-    for (int i = 1; i < nseg; ++i) M = fmaxf(M, s_m[i]);
-    float sm = 0.f;
-    for (int i = 0; i < nseg; ++i) sm += s_s[i] * ex2_approx((s_m[i] - M) * LOG2E);
-    int tot = 0;
-    for (int i = 0; i < nseg; ++i) { const int c = s_off[i + 1]; s_off[i + 1] = tot + c; tot += c; if (c > f.cap) s_bad = 1; }
-    s_off[0] = 0; s_max = M; s_sum = sm; s_n = tot;
-  }
-  __syncthreads();
-  const int n = s_n;
-  if (s_bad || n < k || n > SMP_CAP) {
-    // the sampled threshold missed (or a list overflowed): this row goes through the materialised path (fallback kernels of this step)
-    if (tid == 0) {
-      const int slot = atomicAdd(f.fb_count, 1);
-      atomicAdd(f.status, 1);
-      if (slot < f.fb_cap) f.fb_rows[slot] = (int)r; else f.status[1] = 1;
-      s_slot = slot;
+  if (warp == 0) {
+    // merge the softmax partials and lay the segments out (one warp: shuffles instead of a serial walk over up to 128 segments)
+    float M = -FLT_MAX;
+    for (int i = lane; i < nseg; i += 32) M = fmaxf(M, s_m[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+    float sm = 0.f; int tot = 0, base = 0;
+    for (int i0 = 0; i0 < nseg; i0 += 32) {
+      const int i = i0 + lane;
+      const int c = i < nseg ? s_cnt[i] : 0, cp = (c + 1) & ~1;                // even slots per segment
+      if (i < nseg) sm += s_s[i] * ex2_approx((s_m[i] - M) * LOG2E);
+      int incl = cp;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      if (i < nseg) s_off[i] = base + incl - cp;
+      base += __shfl_sync(0xffffffffu, incl, 31);
+      tot += c;
     }
-    __syncthreads();
-    const int slot = s_slot;
-    if (slot < f.fb_cap)
-      for (int i = tid; i < f.K / 8; i += SMP_THREADS)
-        reinterpret_cast<uint4*>(f.e_fb + (int64_t)slot * f.K)[i] = reinterpret_cast<const uint4*>(f.e + r * f.K)[i];
-    return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sm += __shfl_xor_sync(0xffffffffu, sm, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
+    if (lane == 0) { s_max = M; s_sum = sm; s_n = tot; s_npad = base; }
   }
-  // gather: warps copy whole segments (g = 16 / nseg warps share a segment when there are fewer segments than warps); a lane's loads are
-  // independent of one another, no per-entry search for the segment
-  {
-    constexpr int NW = SMP_THREADS / 32;
-    const int g = nseg >= NW ? 1 : NW / nseg;                    // warps per segment (nseg is a power of two times LF_SEGS = 2)
-    const int sub = warp % g, stride = 32 * g;
-    for (int sgi = warp / g; sgi < nseg; sgi += NW / g) {
-      const int o = s_off[sgi], c = s_off[sgi + 1] - o;
-      const uint2* src = f.lists + (r * nseg + sgi) * (int64_t)f.cap;
-#pragma unroll 4
-      for (int i = sub * 32 + lane; i < c; i += stride) {
-        uint2 en;
-        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(en.x), "=r"(en.y) : "l"(src + i));
-        lval[o + i] = __uint_as_float(en.x); lidx[o + i] = (int)en.y;
+  __syncthreads();
+  const int n = s_n, npad = s_npad;
+  bool fallback = s_bad || n < k || npad > SMP_CAP;
+  if (!fallback) {
+    if (tid == 0) {
+      mbar_expect_tx(&s_bar, (uint32_t)npad * 8u);
+      for (int i = 0; i < nseg; ++i) {
+        const int cp = (s_cnt[i] + 1) & ~1;
+        if (cp) bulk_load_1d(lst + s_off[i], f.lists + (r * nseg + i) * (int64_t)f.cap, (uint32_t)cp * 8u, &s_bar);
       }
     }
+    mbar_wait(&s_bar, 0);
+    if (tid < nseg && (s_cnt[tid] & 1)) lst[s_off[tid] + s_cnt[tid]] = make_uint2(__float_as_uint(-FLT_MAX), 0x7fffffffu);
+    __syncthreads();
+    int win_v; float win_x;
+    if (sample_from_pairs<MODE>(a, tdiv, lst, npad, k, V, b, pos, sc, s_excl, tid, warp, lane, win_v, win_x)) {
+      if (tid == 0) {
+        if (win_v < 0) { win_v = (int)lst[0].y; win_x = __uint_as_float(lst[0].x); }         // degenerate rows (NaN logits)
+        const float pr = expf(win_x - s_max) / s_sum;
+        if (!a.only_masked || a.ids[(int64_t)b * a.n + pos] == a.mask_id) a.ids[(int64_t)b * a.n + pos] = win_v;
+        a.scores[(int64_t)b * a.n + pos] = 1.0f - pr;
+      }
+      return;
+    }
+    fallback = true;
+  }
+  // the sampled threshold missed, a list overflowed, or too many winners failed the rank test: this row goes through the materialised path
+  // (fallback kernels of this step)
+  if (tid == 0) {
+    const int slot = atomicAdd(f.fb_count, 1);
+    atomicAdd(f.status, 1);
+    if (slot < f.fb_cap) f.fb_rows[slot] = (int)r; else f.status[1] = 1;
+    s_slot = slot;
   }
   __syncthreads();
-  int win_v; float win_x;
-  sample_from_list<MODE>(a, tdiv, lval, lidx, n, k, V, b, pos, sc, tid, warp, lane, win_v, win_x);
-  if (tid == 0) {
-    if (win_v < 0) { win_v = lidx[0]; win_x = lval[0]; }         // degenerate rows (NaN logits)
-    const float pr = expf(win_x - s_max) / s_sum;
-    if (!a.only_masked || a.ids[(int64_t)b * a.n + pos] == a.mask_id) a.ids[(int64_t)b * a.n + pos] = win_v;
-    a.scores[(int64_t)b * a.n + pos] = 1.0f - pr;
-  }
+  const int slot = s_slot;
+  if (slot < f.fb_cap)
+    for (int i = tid; i < f.K / 8; i += SMP_THREADS)
+      reinterpret_cast<uint4*>(f.e_fb + (int64_t)slot * f.K)[i] = reinterpret_cast<const uint4*>(f.e + r * f.K)[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -604,7 +620,7 @@ extern "C" int mmg_logits_fused(const mmg_logits_fused_args* a, void* stream) {
     LfFinish f{};
     f.parts = parts; f.lists = lists; f.S = pl.S; f.cap = pl.cap; f.e = reinterpret_cast<const bf16*>(a->e); f.K = a->K;
     f.fb_count = fb_count; f.fb_rows = fb_rows; f.e_fb = e_fb; f.fb_cap = LF_FB_CAP; f.status = a->status;
-    static const size_t smem = (size_t)SMP_CAP * 8;
+    static const size_t smem = (size_t)SMP_CAP * 8;      // padded layouts beyond SMP_CAP entries fall back
     static cudaError_t at0 = cudaFuncSetAttribute(logits_finish_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     static cudaError_t at1 = cudaFuncSetAttribute(logits_finish_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     static cudaError_t at2 = cudaFuncSetAttribute(logits_finish_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

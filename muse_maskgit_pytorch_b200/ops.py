@@ -1,5 +1,7 @@
 """Thin tensor-level wrappers over the C-ABI (one Python function per mmg_* entry point).  PyTorch supplies device
 memory and the stream; every number is computed by libmmg.so."""
+import os
+
 import torch
 
 from . import _lib as L
@@ -25,16 +27,58 @@ def _epi(out=None, ldo=0, bias=None, act=0, resid=None, ldr=0, row_stats=None, l
     return e
 
 
+# ---- fp32 on the tensor cores ---------------------------------------------------------------------------------------------
+# precision="fp32" (the token-identical parity mode) runs its matrix products and convolutions on the SAME tcgen05 kernels as the bf16 path:
+# both operands are split into three bf16 terms (mmg_split3) and one bf16 product over 6K columns accumulates the six significant cross
+# terms in fp32.  Shapes the TMA path cannot take (K or N not a multiple of 64) stay on the CUDA-core kernel.  MMG_FP32_TC=0 / fp32_tc(False)
+# forces the CUDA-core kernel everywhere (the round-1 behaviour).
+_FP32_TC = [os.environ.get("MMG_FP32_TC", "1") != "0"]
+
+
+def fp32_tc(enabled=None):
+    """Query / set whether fp32 matrix products run as 3-way bf16 splits on the tensor cores."""
+    if enabled is not None:
+        _FP32_TC[0] = bool(enabled)
+    return _FP32_TC[0]
+
+
+def split3(src2d, side, out=None):
+    """src2d [rows, K] fp32 (row stride allowed) -> [rows, 6K] bf16 terms, ordered for `side` (0 left operand, 1 right operand)."""
+    assert src2d.dtype == torch.float32 and src2d.dim() == 2 and src2d.stride(1) == 1
+    rows, K = src2d.shape
+    if out is None:
+        out = torch.empty((rows, 6 * K), device=src2d.device, dtype=torch.bfloat16)
+    a = L.Split3Args()
+    a.src = src2d.data_ptr(); a.dst = out.data_ptr(); a.rows = rows; a.K = K; a.lds = src2d.stride(0) if rows > 1 else K; a.side = side
+    L.call("mmg_split3", a)
+    return out
+
+
+def _split_weight(w, rows, K):
+    """Right-operand split of a packed weight viewed as [rows, K], cached on the tensor (dropped with it; redone after in-place edits)."""
+    c = getattr(w, "_mmg_split3", None)
+    if c is not None and c[0] == (w.data_ptr(), w._version, rows, K):
+        return c[1]
+    s3 = split3(w.reshape(rows, K), 1)
+    try:
+        w._mmg_split3 = ((w.data_ptr(), w._version, rows, K), s3)
+    except AttributeError:
+        pass
+    return s3
+
+
 def linear(a, w, out, epilogue=EPI_STORE, bias=None, act=0, resid=None, M=None, N=None, epi=None, row_stats=None, ln_width=0,
            ln_out=None, ln_gamma=None, ln_gamma_b=None, ln_add=None, ln_split=None):
     """out = a @ w.T (+ epilogue).  a [M, K], w [N, K] same dtype (bf16 -> tcgen05, fp32 -> CUDA cores)."""
     _chk(a, "a"); _chk(w, "w")
+    assert w.shape[1] == a.shape[1] and a.dtype == w.dtype
+    if a.dtype == torch.float32 and _FP32_TC[0] and a.shape[1] % 64 == 0 and (w.shape[0] if N is None else N) % 64 == 0 and a.shape[0] > 0:
+        a, w = split3(a, 0), _split_weight(w, w.shape[0], w.shape[1])          # same product, 6K bf16 columns, fp32 accumulation in TMEM
     args = L.LinearArgs()
     args.a = a.data_ptr(); args.w = w.data_ptr()
     args.M = a.shape[0] if M is None else M
     args.N = w.shape[0] if N is None else N
     args.K = a.shape[1]; args.lda = a.stride(0); args.ldw = w.stride(0)
-    assert w.shape[1] == a.shape[1] and a.dtype == w.dtype
     args.dtype = L.dt(a); args.epilogue = epilogue
     if epi is None:
         epi = _epi(out, out.stride(0), bias, act, resid, resid.stride(0) if resid is not None else 0, row_stats, ln_width)
@@ -64,6 +108,9 @@ def qkv_epilogue(dtype_t, heads, tokens, q=None, k=None, v=None, q_scale=None, k
 def conv2d(x, w, out, B, H, W, Cin, Cout, kind, epilogue=EPI_STORE, bias=None, act=0, resid=None):
     """x [B,H,W,Cin] NHWC, w packed [Cout, taps*Cin]; out rows = output pixels."""
     _chk(x); _chk(w)
+    if x.dtype == torch.float32 and _FP32_TC[0] and Cin % 32 == 0 and Cout % 64 == 0 and kind != 3:
+        # per-pixel / per-tap split: 6*Cin channels (a multiple of 64), the same implicit GEMM
+        x, w, Cin = split3(x.reshape(-1, Cin), 0), _split_weight(w, w.numel() // Cin, Cin), 6 * Cin
     a = L.Conv2dArgs()
     a.x = x.data_ptr(); a.w = w.data_ptr(); a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.kind = kind
     a.dtype = L.dt(x); a.epilogue = epilogue
@@ -76,6 +123,8 @@ def conv2d(x, w, out, B, H, W, Cin, Cout, kind, epilogue=EPI_STORE, bias=None, a
 def conv_transpose2d(x, w, out, B, H, W, Cin, Cout, bias=None, rgb_w=None, rgb_b=None):
     """ConvTranspose2d(4,2,1) + LeakyReLU(0.1); with rgb_w: fused trailing 1x1 conv, out fp32 [B, ch, 2H, 2W]."""
     _chk(x); _chk(w)
+    if x.dtype == torch.float32 and _FP32_TC[0] and Cin % 32 == 0 and Cout % 64 == 0:
+        x, w, Cin = split3(x.reshape(-1, Cin), 0), _split_weight(w, w.numel() // Cin, Cin), 6 * Cin
     a = L.ConvTranspose2dArgs()
     a.x = x.data_ptr(); a.w = w.data_ptr(); a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout
     a.dtype = L.dt(x)
@@ -134,9 +183,15 @@ def embed(ids, token_emb, pos_emb, x, n, copies=1, use_pos=True):
 def attention(q, k, v, out, B, heads, Tk, key_mask=None, kv_shared=False, scale=8.0, logit_bound=0.0):
     """q [B*heads, Tq, 64]; k, v [(B or 1)*heads, Tk_alloc, 64]; out [B*Tq, heads*64]."""
     a = L.AttentionArgs()
-    a.q = _chk(q).data_ptr(); a.k = _chk(k).data_ptr(); a.v = _chk(v).data_ptr(); a.out = out.data_ptr()
+    _chk(q); _chk(k); _chk(v)
+    Tq, Tk_alloc, dtype = q.shape[1], k.shape[1], L.dt(q)
+    if q.dtype == torch.float32 and _FP32_TC[0] and Tk <= 4096 and out.dtype == torch.float32 and out.stride(0) % 4 == 0:
+        # fp32 parity on the tensor cores: three bf16 terms per operand, six cross terms per product (mmg_attention_split.cuh)
+        q, k, v = split3(q.view(-1, 64), 0), split3(k.view(-1, 64), 1), split3(v.view(-1, 64), 1)
+        dtype = L.BF16; a.split3 = 1
+    a.q = q.data_ptr(); a.k = k.data_ptr(); a.v = v.data_ptr(); a.out = out.data_ptr()
     a.key_mask = L.ptr(key_mask)
-    a.B = B; a.heads = heads; a.Tq = q.shape[1]; a.Tk = Tk; a.Tk_alloc = k.shape[1]; a.dtype = L.dt(q)
+    a.B = B; a.heads = heads; a.Tq = Tq; a.Tk = Tk; a.Tk_alloc = Tk_alloc; a.dtype = dtype
     a.ldo = out.stride(0); a.kv_batch_stride_zero = int(kv_shared); a.scale = scale; a.logit_bound = logit_bound
     L.call("mmg_attention", a)
     return out

@@ -38,13 +38,16 @@ def read():
 
 
 def report(name, fn, tiles_per_cta):
+    lib.mmg_trace_clear()
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     t = read()[:148, :min(tiles_per_cta, NT)]
-    if os.environ.get("MMG_GEMM_PAIR") == "1":
+    pair = bool((t[1::2, :2, 3] == 0).all()) or os.environ.get("MMG_GEMM_PAIR") == "1"
+    if pair:
         lead = t[0::2]                     # MMA slots are written by the leader CTA of each pair only
         t = t.copy(); t[1::2, :, 0:4] = lead[:, :, 0:4]
+        name += " [CTA pairs]"
     n = t.shape[1]
     # slots: 0 mma tile start, 1 after tmem_empty wait, 2 sum full-bar wait, 3 after last commit, 4 epi before tmem_full wait,
     #        5 after, 6 release, 7 epi end, 8 producer sum empty wait, 9 producer tile end
@@ -79,25 +82,25 @@ def W(n, k):
 
 # plain bf16 store at the qkv shape
 w = W(1536, 512); out = torch.empty(M, 1536, device=dev, dtype=bf)
-report("store bf16  32768x1536x512", lambda: ops.linear(x, w, out), 11)
+report("store bf16  32768x1536x512", lambda: ops.linear(x, w, out), 10)
 # QKV epilogue
 heads, n = 8, 256
 q = torch.empty(M // n * heads, n, 64, device=dev, dtype=bf); k = torch.zeros(M // n * heads, 264, 64, device=dev, dtype=bf); v = torch.zeros_like(k)
 qs = torch.ones(64, device=dev); nk = torch.zeros(heads, 64, device=dev, dtype=bf)
 epi = ops.qkv_epilogue(bf, heads, n, q=q, k=k, v=v, q_scale=qs, k_scale=qs, key_off=1, null_k=nk, null_v=nk)
-report("qkv         32768x1536x512", lambda: ops.linear(x, w, None, epilogue=ops.EPI_QKV, epi=epi), 11)
+report("qkv         32768x1536x512", lambda: ops.linear(x, w, None, epilogue=ops.EPI_QKV, epi=epi), 10)
 # residual fp32
 w2 = W(512, 512)
-report("resid f32   32768x512x512", lambda: ops.linear(x, w2, xf, epilogue=ops.EPI_RESIDUAL, resid=xf), 4)
+report("resid f32   32768x512x512", lambda: ops.linear(x, w2, xf, epilogue=ops.EPI_RESIDUAL, resid=xf), 3)
 # GEGLU
 w1 = W(2816, 512); hh = torch.empty(M, 1408, device=dev, dtype=bf)
-report("geglu       32768x2816x512", lambda: ops.linear(x, w1, hh, epilogue=ops.EPI_GEGLU), 20)
+report("geglu       32768x2816x512", lambda: ops.linear(x, w1, hh, epilogue=ops.EPI_GEGLU), 19)
 # ff2 residual
 w3 = W(512, 1408)
-report("resid f32   32768x512x1408", lambda: ops.linear(h, w3, xf, epilogue=ops.EPI_RESIDUAL, resid=xf), 4)
+report("resid f32   32768x512x1408", lambda: ops.linear(h, w3, xf, epilogue=ops.EPI_RESIDUAL, resid=xf), 3)
 # logits
 wl = W(65536, 512); e = torch.randn(10240, 512, device=dev).to(bf); lg = torch.empty(10240, 65536, device=dev)
 report("logits f32  10240x65536x512", lambda: ops.linear(e, wl, lg), 32)
 # long K reference
 a8 = torch.randn(8192, 8192, device=dev).to(bf); w8 = W(8192, 8192); o8 = torch.empty(8192, 8192, device=dev, dtype=bf)
-report("store bf16  8192^3", lambda: ops.linear(a8, w8, o8), 14)
+report("store bf16  8192^3", lambda: ops.linear(a8, w8, o8), 13)

@@ -631,3 +631,59 @@ def test_logits_sample_any_topk_threshold(thres, temp):
     ok = margin > 1e-4
     assert torch.equal(got[ok], pred[ok]), (got.tolist(), pred.tolist(), margin.tolist())
     assert torch.allclose(gsc[got == pred], score[got == pred], atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------ fp32 on the tensor cores (3-way bf16 split)
+def test_split3_terms_reconstruct_fp32():
+    """mmg_split3: hi + mid + lo == x to 2^-24 relative, every term a bf16 value, operand orders as documented in include/mmg.h."""
+    x = rnd("s3", (70, 192)) * torch.from_numpy(synth.normal("s3e", (70, 192), 5, 3.0)).exp()       # wide dynamic range
+    for side, order in ((0, "LHMMHH"), (1, "HLMHMH")):
+        s = ops().split3(dev(x), side).float().cpu().view(70, 6, 192)
+        hi = x.to(torch.bfloat16).float(); r1 = x - hi; mid = r1.to(torch.bfloat16).float(); lo = (r1 - mid).to(torch.bfloat16).float()
+        terms = {"H": hi, "M": mid, "L": lo}
+        for t, ch in enumerate(order):
+            assert torch.equal(s[:, t], terms[ch]), (side, t)
+        assert ((hi + mid + lo - x).abs() <= x.abs() * 2.0 ** -23).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 512), (300, 192, 128), (1024, 2816, 512), (512, 512, 1408)])
+def test_linear_fp32_tensor_core_split_vs_fp64(M, N, K):
+    """precision='fp32' products run as 6K-wide bf16 products on tcgen05: error vs an fp64 reference at the level of the fp32 CUDA-core kernel."""
+    a, w = rnd(f"a{M}{K}", (M, K)), rnd(f"w{N}{K}", (N, K), std=K ** -0.5)
+    ref = (a.double() @ w.double().t())
+    o = ops()
+    was = o.fp32_tc()
+    try:
+        errs = {}
+        for mode in (True, False):
+            o.fp32_tc(mode)
+            out = torch.empty((M, N), device="cuda", dtype=torch.float32)
+            o.linear(dev(a), dev(w), out)
+            errs[mode] = float((out.cpu().double() - ref).abs().max())
+    finally:
+        o.fp32_tc(was)
+    print(f"max |err| vs fp64: tensor-core split {errs[True]:.3e}, CUDA-core fp32 {errs[False]:.3e}")
+    assert errs[True] <= max(4 * errs[False], 2e-6), errs
+
+
+def test_conv2d_fp32_tensor_core_split_vs_fp64():
+    B, H, W, Cin, Cout = 2, 16, 16, 64, 128
+    x, wt, bias = rnd("cx", (B, Cin, H, W)), rnd("cw", (Cout, Cin, 3, 3), std=(9 * Cin) ** -0.5), rnd("cb", (Cout,))
+    ref = F.conv2d(x.double(), wt.double(), bias.double(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    o = ops()
+    xh = dev(x.permute(0, 2, 3, 1).contiguous())
+    wp = dev(wt.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous())
+    was = o.fp32_tc()
+    try:
+        errs = {}
+        for mode in (True, False):
+            o.fp32_tc(mode)
+            out = torch.empty((B * H * W, Cout), device="cuda", dtype=torch.float32)
+            o.conv2d(xh, wp, out, B, H, W, Cin, Cout, 1, bias=dev(bias))
+            errs[mode] = float((out.cpu().double() - ref).abs().max())
+    finally:
+        o.fp32_tc(was)
+    print(f"max |err| vs fp64: tensor-core split {errs[True]:.3e}, CUDA-core fp32 {errs[False]:.3e}")
+    # the tensor core adds into its fp32 accumulator with truncation (up to ~1 ulp per K = 16 step, 216 steps here) where the CUDA-core kernel
+    # rounds to nearest: the bound is in ulps of the output range, not relative to the CUDA-core error
+    assert errs[True] <= 3e-5 * float(ref.abs().max()), errs
