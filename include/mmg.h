@@ -94,9 +94,11 @@ typedef struct {
    * to_out(null_v)).  The two CTAs that own the halves of a row exchange (sum, sumsq) through distributed shared memory.  */
   void*        ln_out; int64_t ld_ln;
   const float* ln_gamma; const float* ln_gamma_b; const float* ln_add; int64_t ln_split;
-  float*       row_stats;  /* [M, 2] fp32 (sum, sum of squares). GEGLU: the epilogue atomically ACCUMULATES its fp32 outputs;
-                              LNFOLD_RESIDUAL: read (statistics over ln_width columns, eps 1e-5)                       */
-  int32_t      ln_width; int32_t _pad0;
+  float*       row_stats;  /* [M, stats_slots, 2] fp32 (sum, sum of squares) partials.  GEGLU: the epilogue WRITES the statistics of each
+                              64-column accumulator chunk (32 outputs, as rounded to out_dtype) to slot col / 64 (stats_slots >= N / 64;
+                              every slot of every row is written exactly once, no atomics); LNFOLD_RESIDUAL: adds the stats_slots partials
+                              of its row in ascending order (statistics over ln_width columns, eps 1e-5) — bitwise reproducible           */
+  int32_t      ln_width; int32_t stats_slots;
   const float* rgb_w;      /* CONVT_RGB: [channels, N] fp32 1x1 weights, rgb_b [channels]                          */
   const float* rgb_b;
   int32_t      rgb_channels;
@@ -167,7 +169,8 @@ typedef struct {
   const float* gamma;      /* [width]                                                                            */
   const float* add;        /* [width] or NULL                                                                    */
   float*       x_out;      /* fp32 [rows, ldx] or NULL                                                           */
-  float*       zero_stats; /* optional [rows, 2]: reset to 0 (row statistics accumulated by a later GEGLU epilogue)     */
+  float*       zero_stats; /* optional [rows, 2]: reset to 0 (kept for callers that accumulate their own row statistics; the GEGLU
+                              epilogue writes per-chunk partials and needs no reset)                                          */
   int64_t      add_from;   /* `add` / `x_out` apply to rows >= add_from only (null-CFG branch rows of a 2-branch batch)   */
   int64_t rows, width, ldx, ldy;
 } mmg_layernorm_args;
@@ -332,7 +335,7 @@ typedef struct {
   const void* w1;                                 /* [2*Fp, dim] bf16, rows interleaved in blocks of 32: [x(32) | gate(32)] */
   const void* w2f; const float* cvec;             /* [dim, Fp] bf16, [dim]                                                  */
   const float* add; int64_t add_from;             /* optional [dim] constant (to_out(null_v) of an all-masked cross-attention) */
-  void* xn; void* h; float* stats;                /* workspace: [rows, dim] bf16, [rows, Fp] bf16, [rows, 2] fp32            */
+  void* xn; void* h; float* stats;                /* workspace: [rows, dim] bf16, [rows, Fp] bf16, [rows, Fp / 32, 2] fp32   */
 } mmg_ff_geglu_args;
 int mmg_ff_geglu(const mmg_ff_geglu_args* a, void* stream);
 

@@ -11,7 +11,7 @@ struct Epilogue {
   int fast;                 // 1: tensor-core (bf16) path — MUFU-based erf/sigmoid are accurate far beyond bf16 output precision
   int64_t M, N;
   float rgb_acc[4];
-  float st_a, st_b;         // GEGLU: partial (sum, sumsq) of this thread's outputs; LNFOLD: (mean, rstd) of the row
+  float st_a, st_b;         // LNFOLD: (mean, rstd) of the row
   int r_b, r_t;             // QKV: (batch, token) of the row; CONVT*: (batch, y * W + x)
   template <typename T>
   static __device__ __forceinline__ void store_n(T* dst, const float (&v)[64], int n, bool vec_ok) {
@@ -37,11 +37,13 @@ struct Epilogue {
   __device__ __forceinline__ void begin_row(int64_t row) {
     if (kind == MMG_EPI_QKV) { const uint32_t r = (uint32_t)row, d = (uint32_t)p.tokens; r_b = (int)(r / d); r_t = (int)(r - (uint32_t)r_b * d); }
     if (kind == MMG_EPI_CONVT || kind == MMG_EPI_CONVT_RGB) { const uint32_t r = (uint32_t)row, d = (uint32_t)(p.H * p.W); r_b = (int)(r / d); r_t = (int)(r - (uint32_t)r_b * d); }
-    if (kind == MMG_EPI_GEGLU) { st_a = 0.f; st_b = 0.f; }
     if (kind == MMG_EPI_LNFOLD_RESIDUAL) {
-      const float2 s = *reinterpret_cast<const float2*>(p.row_stats + 2 * row);
-      const float mean = s.x / (float)p.ln_width;
-      st_a = mean; st_b = rsqrtf(fmaxf(s.y / (float)p.ln_width - mean * mean, 0.f) + 1e-5f);
+      // the row's (sum, sumsq) = its per-chunk partials added in ascending chunk order: the same bits whichever CTA wrote which partial when
+      const float2* sp = reinterpret_cast<const float2*>(p.row_stats) + row * (int64_t)p.stats_slots;
+      float sx = 0.f, sq = 0.f;
+      for (int i = 0; i < p.stats_slots; ++i) { const float2 t = __ldg(sp + i); sx += t.x; sq += t.y; }
+      const float mean = sx / (float)p.ln_width;
+      st_a = mean; st_b = rsqrtf(fmaxf(sq / (float)p.ln_width - mean * mean, 0.f) + 1e-5f);
     }
     if (kind == MMG_EPI_CONVT_RGB) {
 #pragma unroll
@@ -88,14 +90,24 @@ struct Epilogue {
     }
   }
 
-  // GEGLU of one 64-column accumulator chunk [x(32) | gate(32)] -> 32 outputs (+ the row statistics of the folded LayerNorm)
+  // GEGLU of one 64-column accumulator chunk [x(32) | gate(32)] -> 32 outputs.  With row_stats: this chunk's (sum, sumsq) of the outputs goes
+  // to its own slot row_stats[row][col0 / 64] (no atomics: the folded LayerNorm adds the slots in a fixed order, so bf16 generate() is bitwise
+  // reproducible whatever the tile schedule).  The statistics are those of the bf16-ROUNDED outputs when the output is bf16 — the values the
+  // second product consumes.
   template <bool FAST>
-  __device__ __forceinline__ void geglu_chunk(const float (&v)[64], float (&o)[32]) {
+  __device__ __forceinline__ void geglu_chunk(const float (&v)[64], float (&o)[32], int64_t row, int col0, bool write_stats) const {
 #pragma unroll
     for (int i = 0; i < 32; ++i) o[i] = v[32 + i] * (FAST ? gelu_fast(v[i]) : gelu_erf(v[i]));
-    if (p.row_stats) {
+    if (p.row_stats && write_stats) {
+      float sx = 0.f, sq = 0.f;
+      if (p.out_dtype == MMG_BF16) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { st_a += o[i]; st_b = fmaf(o[i], o[i], st_b); }
+        for (int i = 0; i < 32; ++i) { const float t = __bfloat162float(__float2bfloat16_rn(o[i])); sx += t; sq = fmaf(t, t, sq); }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { sx += o[i]; sq = fmaf(o[i], o[i], sq); }
+      }
+      reinterpret_cast<float2*>(p.row_stats)[row * (int64_t)p.stats_slots + (col0 >> 6)] = make_float2(sx, sq);
     }
   }
 
@@ -185,7 +197,7 @@ struct Epilogue {
       case MMG_EPI_GLU: {
         float o[32];
         if (kind == MMG_EPI_GEGLU) {
-          geglu_chunk<FAST>(v, o);
+          geglu_chunk<FAST>(v, o, row, col0, true);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -293,7 +305,6 @@ struct Epilogue {
   }
 
   __device__ __forceinline__ void end_row(int64_t row) {
-    if (kind == MMG_EPI_GEGLU && p.row_stats) { atomicAdd(p.row_stats + 2 * row, st_a); atomicAdd(p.row_stats + 2 * row + 1, st_b); }
     if (kind == MMG_EPI_CONVT_RGB) {
       const int64_t b = r_b; const int rem = r_t; const int y = rem / p.W, x = rem - y * p.W;
       const int oy = 2 * y + p.py, ox = 2 * x + p.px;
@@ -313,10 +324,13 @@ inline int validate_epilogue(int kind, const mmg_epilogue_args& e, int64_t N) {
     case MMG_EPI_LFQ_IDS: MMG_CHECK_ARG(e.out && N == 64 && e.ln_width >= 1 && 3 * e.ln_width <= 64, "epilogue LFQ_IDS: N must be 64 and 3*bits <= 64"); break;
     case MMG_EPI_ARGMIN: MMG_CHECK_ARG(e.out && e.bias, "epilogue ARGMIN: out / code norms NULL"); break;
     case MMG_EPI_LNFOLD_RESIDUAL:
-      MMG_CHECK_ARG(e.out && e.resid && e.bias && e.row_stats && e.ln_width > 0, "epilogue LNFOLD_RESIDUAL: out/resid/cvec/row_stats/ln_width");
+      MMG_CHECK_ARG(e.out && e.resid && e.bias && e.row_stats && e.ln_width > 0 && e.stats_slots >= 1, "epilogue LNFOLD_RESIDUAL: out/resid/cvec/row_stats/ln_width/stats_slots");
       MMG_CHECK_ARG(e.out_dtype == MMG_F32 && (N % 64) == 0 && (e.ldo % 4) == 0 && (e.ldr % 4) == 0, "epilogue LNFOLD_RESIDUAL: fp32 out, N %% 64, ld %% 4");
       break;
-    case MMG_EPI_GEGLU: case MMG_EPI_GLU: MMG_CHECK_ARG(e.out && (N % 64) == 0, "epilogue GEGLU/GLU: N %% 64 != 0 or out NULL"); break;
+    case MMG_EPI_GEGLU: case MMG_EPI_GLU:
+      MMG_CHECK_ARG(e.out && (N % 64) == 0, "epilogue GEGLU/GLU: N %% 64 != 0 or out NULL");
+      MMG_CHECK_ARG(!e.row_stats || (int64_t)e.stats_slots * 64 >= N, "epilogue GEGLU: row_stats needs stats_slots >= N / 64 (%d slots for N = %lld)", e.stats_slots, (long long)N);
+      break;
     case MMG_EPI_QKV:
       MMG_CHECK_ARG((N % 64) == 0 && N / 64 == e.nq_heads + e.nk_heads + e.nv_heads, "epilogue QKV: N != 64*(nq+nk+nv)");
       MMG_CHECK_ARG(e.tokens > 0 && e.heads > 0, "epilogue QKV: tokens/heads");

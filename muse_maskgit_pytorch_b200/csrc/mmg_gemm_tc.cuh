@@ -273,12 +273,12 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       float rbuf[64];
       float ln_sum = 0.f, ln_sq = 0.f;
       if (pre) epi.load_resid(row, n_blk * BN + c_first * 64, rbuf);      // in flight while the MMA of this tile completes
+      if (valid && mine) epi.begin_row(row);                               // row geometry / folded-LayerNorm statistics: independent of the accumulator
       if (tr) MMG_TR(4, MMG_CLK());
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       if (tr) MMG_TR(5, MMG_CLK());
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      if (valid && mine) epi.begin_row(row);
       bool released = false;
 #pragma unroll 1
       for (int c = c_first; c < c_end; c += c_step) {
@@ -298,7 +298,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         if (GEGLUT) {
           // columns past N are zero accumulators (TMA zero-fills the missing W rows) and are clipped by the tensor map, rows past M too
           float o[32];
-          epi.template geglu_chunk<true>(v, o);
+          epi.template geglu_chunk<true>(v, o, row, col0, valid && col0 < p.N);
           const uint32_t wtile = smem_u32(smem + STAGES * STAGE_BYTES + 1024) + (uint32_t)(warp - 4) * 4096u;
           const int cc = c - c_first;                       // 0 / 1: left / right 64 bytes of the warp's 128-byte rows
           if (cc == 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }     // this warp's previous store has left the tile
@@ -394,8 +394,6 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) { ts += s_part[stats_buf][rk][r_in_tile][hf][0]; tq += s_part[stats_buf][rk][r_in_tile][hf][1]; }
         stats_buf ^= 1;
-        if (valid && my_rank == 0 && half == 0 && epi.kind == MMG_EPI_RESIDUAL && epi.p.row_stats)      // reset the statistics the next GEGLU epilogue accumulates
-          *reinterpret_cast<float2*>(epi.p.row_stats + 2 * row) = make_float2(0.f, 0.f);
         if (valid) {
           const float inv_n = 1.0f / (float)p.N;
           const float mean = ts * inv_n;

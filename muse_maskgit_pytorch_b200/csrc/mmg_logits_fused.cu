@@ -348,25 +348,49 @@ struct LfFinish {
   int* status;                                // [0] += fallback rows, [1] = 1 when more rows than fb_cap needed the fallback
 };
 
-// Finisher.  One CTA per row.  The row's candidate segments (~62 KB, interleaved (logit, index) pairs) come into shared memory as ONE bulk
-// copy per segment (cp.async.bulk -> mbarrier: no registers, no per-thread round trips; the first version's per-lane 8-byte loads kept 16 KB
-// in flight per CTA and ran at 0.86 TB/s, 15 % of a generate()); the selection keeps no per-candidate registers (sample_from_pairs), so two
-// CTAs share an SM and one row's copy overlaps the other's Philox / gumbel pass.  Segments are placed at even entry offsets (16-byte aligned
-// destinations); an odd segment drags one foreign entry along, which is overwritten with padding.
+// Finisher.  One CTA of LFN_THREADS per row, nothing but a few words of shared memory, so 6-8 CTAs share an SM and one row's memory round trips
+// hide under the others' Philox / gumbel arithmetic.  The row's candidate segments (~62 KB of interleaved (logit, index) pairs) are STREAMED:
+//   pass 1  every candidate: noise -> perturbed value, each thread keeps only its best; block argmax -> winner (ties -> lowest vocabulary index)
+//   pass 2  (the same bytes again, now L2 hits) exact rank of the winner's logit inside the row: the list covers everything >= it
+// and if the winner fails the rank test (it lies between the candidate threshold and the true k-th value: the list holds ~ k + 4 sigma
+// entries) its index joins a small exclusion list and pass 1 is repeated — the noise is a pure function of (row, vocabulary index), so the
+// repeat reproduces the same values and the result equals sample_from_list's on the gathered list.  (First version: one 512-thread CTA per row
+// gathered the list into 74 KB of shared memory with per-lane 8-byte loads, two CTAs per SM: 0.86 TB/s, 15 % of a generate().)
+constexpr int LFN_THREADS = 256;
+constexpr int LFN_MAX_EXCL = 24;
+
+// candidate traversal shared by both passes: warp w of NW takes segments w, w + NW, ... when there are at least NW segments, otherwise
+// NW / nseg warps share a segment; a lane reads two entries (16 bytes) per load, two loads in flight
+template <typename F>
+__device__ __forceinline__ void lfn_for_each(const uint2* __restrict__ row_lists, const int* s_cnt, int nseg, int cap, int warp, int lane, F&& fn) {
+  constexpr int NW = LFN_THREADS / 32;
+  const int g = nseg >= NW ? 1 : NW / nseg;                      // warps per segment (nseg = 2 x a power of two)
+  const int sub = warp % g, stride = 64 * g;
+  for (int sgi = warp / g; sgi < nseg; sgi += NW / g) {
+    const int c = s_cnt[sgi];
+    const uint2* src = row_lists + (int64_t)sgi * cap;
+    for (int i = (sub * 32 + lane) * 2; i < c; i += 2 * stride) {
+      uint4 e0, e1 = make_uint4(0u, 0u, 0u, 0u);
+      const int i1 = i + stride;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e0.x), "=r"(e0.y), "=r"(e0.z), "=r"(e0.w) : "l"(src + i));
+      if (i1 < c) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e1.x), "=r"(e1.y), "=r"(e1.z), "=r"(e1.w) : "l"(src + i1));
+      fn(e0.x, e0.y); if (i + 1 < c) fn(e0.z, e0.w);
+      if (i1 < c) { fn(e1.x, e1.y); if (i1 + 1 < c) fn(e1.z, e1.w); }
+    }
+  }
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(SMP_THREADS, 2)
+__global__ void __launch_bounds__(LFN_THREADS, 6)
 logits_finish_kernel(const mmg_logits_sample_args a, float tdiv, const LfFinish f) {
-  using namespace sm100;
-  extern __shared__ __align__(16) uint8_t smraw[];
-  uint2* lst = reinterpret_cast<uint2*>(smraw);                  // [SMP_CAP + 2 * segments]
-  __shared__ SampleScratch sc;
-  __shared__ int s_off[LF_SEGS * LF_MAX_SPLITS + 1], s_cnt[LF_SEGS * LF_MAX_SPLITS];
+  __shared__ int s_cnt[LF_SEGS * LF_MAX_SPLITS];
   __shared__ float s_m[LF_SEGS * LF_MAX_SPLITS], s_s[LF_SEGS * LF_MAX_SPLITS];
   __shared__ float s_max, s_sum;
-  __shared__ int s_n, s_npad, s_bad, s_slot;
-  __shared__ int s_excl[SMP_MAX_EXCL];
-  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_n, s_bad, s_slot;
+  __shared__ int s_excl[LFN_MAX_EXCL];
+  __shared__ float s_rv[LFN_THREADS / 32]; __shared__ int s_ri[LFN_THREADS / 32]; __shared__ uint32_t s_rx[LFN_THREADS / 32]; __shared__ int s_rc[LFN_THREADS / 32];
   constexpr float LOG2E = 1.4426950408889634f;
+  constexpr int NW = LFN_THREADS / 32;
 
   pdl_wait(); pdl_trigger();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -375,7 +399,7 @@ logits_finish_kernel(const mmg_logits_sample_args a, float tdiv, const LfFinish 
   const int b = (int)(r / a.num_masked);
   const int pos = a.masked_pos[r];
   const int nseg = LF_SEGS * f.S;
-  if (tid == 0) { s_bad = 0; mbar_init(&s_bar, 1); fence_barrier_init(); }
+  if (tid == 0) s_bad = 0;
   __syncthreads();
   if (tid < nseg) {
     const float4 pt = f.parts[r * nseg + tid];
@@ -383,53 +407,99 @@ logits_finish_kernel(const mmg_logits_sample_args a, float tdiv, const LfFinish 
     if (__float_as_int(pt.w) || __float_as_int(pt.z) > f.cap) s_bad = 1;
   }
   __syncthreads();
-  if (warp == 0) {
-    // merge the softmax partials and lay the segments out (one warp: shuffles instead of a serial walk over up to 128 segments)
+  if (warp == 0) {                                                // merge the softmax partials of the segments
     float M = -FLT_MAX;
     for (int i = lane; i < nseg; i += 32) M = fmaxf(M, s_m[i]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
-    float sm = 0.f; int tot = 0, base = 0;
-    for (int i0 = 0; i0 < nseg; i0 += 32) {
-      const int i = i0 + lane;
-      const int c = i < nseg ? s_cnt[i] : 0, cp = (c + 1) & ~1;                // even slots per segment
-      if (i < nseg) sm += s_s[i] * ex2_approx((s_m[i] - M) * LOG2E);
-      int incl = cp;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-      if (i < nseg) s_off[i] = base + incl - cp;
-      base += __shfl_sync(0xffffffffu, incl, 31);
-      tot += c;
-    }
+    float sm = 0.f; int tot = 0;
+    for (int i = lane; i < nseg; i += 32) { sm += s_s[i] * ex2_approx((s_m[i] - M) * LOG2E); tot += s_cnt[i]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { sm += __shfl_xor_sync(0xffffffffu, sm, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
-    if (lane == 0) { s_max = M; s_sum = sm; s_n = tot; s_npad = base; }
+    if (lane == 0) { s_max = M; s_sum = sm; s_n = tot; }
   }
   __syncthreads();
-  const int n = s_n, npad = s_npad;
-  bool fallback = s_bad || n < k || npad > SMP_CAP;
+  const int n = s_n;
+  bool fallback = s_bad || n < k;
   if (!fallback) {
-    if (tid == 0) {
-      mbar_expect_tx(&s_bar, (uint32_t)npad * 8u);
-      for (int i = 0; i < nseg; ++i) {
-        const int cp = (s_cnt[i] + 1) & ~1;
-        if (cp) bulk_load_1d(lst + s_off[i], f.lists + (r * nseg + i) * (int64_t)f.cap, (uint32_t)cp * 8u, &s_bar);
-      }
+    const uint2* row_lists = f.lists + r * (int64_t)nseg * f.cap;
+    const int64_t grow = a.row_offset + (int64_t)b * a.n + pos;
+    const uint64_t seed = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
+    const float inv_t = 1.0f / tdiv;
+    uint64_t aq0 = 0, aoff4 = 0; uint32_t ar0 = 0;
+    if (MODE == 2) {            // flat index of logit (grow, v) in the reference's [B, n, V] noise tensor = grow * V + v = ar0 + v + S * aq0
+      const uint64_t base = (uint64_t)grow * (uint64_t)V;
+      aq0 = base / a.aten_stride; ar0 = (uint32_t)(base - aq0 * a.aten_stride);
+      aoff4 = (a.aten_offset + (a.aten_offset_dev ? *a.aten_offset_dev : 0ull)) >> 2;
     }
-    mbar_wait(&s_bar, 0);
-    if (tid < nseg && (s_cnt[tid] & 1)) lst[s_off[tid] + s_cnt[tid]] = make_uint2(__float_as_uint(-FLT_MAX), 0x7fffffffu);
-    __syncthreads();
-    int win_v; float win_x;
-    if (sample_from_pairs<MODE>(a, tdiv, lst, npad, k, V, b, pos, sc, s_excl, tid, warp, lane, win_v, win_x)) {
+    PhiloxRow prow;
+    if (MODE == 0) prow = philox_row((uint32_t)a.step, (uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+    int win_v = -1; float win_x = 0.f;
+    for (int nex = 0; ; ++nex) {
+      // ---- pass 1: perturbed argmax over the candidates that have not failed the rank test
+      float bv = -FLT_MAX; int bi = 0x7fffffff; uint32_t bx = 0;
+      lfn_for_each(row_lists, s_cnt, nseg, f.cap, warp, lane, [&](uint32_t xb, uint32_t vb) {
+        const int v = (int)vb;
+        bool skip = false;
+        for (int e = 0; e < nex; ++e) skip |= s_excl[e] == v;
+        if (skip) return;
+        const float x = __uint_as_float(xb);
+        float p;
+        if (MODE != 0) {
+          float u;
+          if (MODE == 1) u = a.u[((int64_t)b * a.n + pos) * V + v];
+          else { const uint32_t q = ar0 + (uint32_t)v, dq = q / a.aten_stride; u = aten_uniform(q - dq * a.aten_stride, aq0 + dq, aoff4, seed); }
+          const float l1 = logf(fmaxf(u, 1e-20f));
+          p = __fdiv_rn(x, tdiv) - logf(fmaxf(-l1, 1e-20f));
+        } else {
+          const float u = (float)(philox_first_row((uint32_t)v, prow) >> 8) * (1.0f / 16777216.0f);
+          const float l1 = __logf(fmaxf(u, 1e-20f));
+          p = fmaf(x, inv_t, -__logf(fmaxf(-l1, 1e-20f)));
+        }
+        if (bi == 0x7fffffff || better(p, v, bv, bi)) { bv = p; bi = v; bx = xb; }
+      });
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o); const uint32_t ox = __shfl_xor_sync(0xffffffffu, bx, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ov, oi, bv, bi))) { bv = ov; bi = oi; bx = ox; }
+      }
+      __syncthreads();                                           // previous round's readers of the scratch are done
+      if (lane == 0) { s_rv[warp] = bv; s_ri[warp] = bi; s_rx[warp] = bx; }
+      __syncthreads();
+      bv = s_rv[0]; bi = s_ri[0]; bx = s_rx[0];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) {
+        const float ov = s_rv[w]; const int oi = s_ri[w];
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ov, oi, bv, bi))) { bv = ov; bi = oi; bx = s_rx[w]; }
+      }
+      if (bi == 0x7fffffff) break;                               // nothing left (degenerate row): win_v stays -1
+      // ---- pass 2: exact rank of the winner's logit inside the row
+      const float cx = __uint_as_float(bx);
+      int c = 0;
+      lfn_for_each(row_lists, s_cnt, nseg, f.cap, warp, lane, [&](uint32_t xb, uint32_t vb) {
+        const float x = __uint_as_float(xb);
+        c += (x > cx) || (x == cx && (int)vb < bi);
+      });
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0) s_rc[warp] = c;
+      __syncthreads();
+      int rank = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) rank += s_rc[w];
+      if (rank < k) { win_v = bi; win_x = cx; break; }
+      if (nex == LFN_MAX_EXCL) { fallback = true; break; }
+      if (tid == 0) s_excl[nex] = bi;
+      __syncthreads();
+    }
+    if (!fallback) {
       if (tid == 0) {
-        if (win_v < 0) { win_v = (int)lst[0].y; win_x = __uint_as_float(lst[0].x); }         // degenerate rows (NaN logits)
+        if (win_v < 0) { const uint2 e0 = row_lists[0]; win_v = (int)e0.y; win_x = __uint_as_float(e0.x); }    // degenerate rows (NaN logits)
         const float pr = expf(win_x - s_max) / s_sum;
         if (!a.only_masked || a.ids[(int64_t)b * a.n + pos] == a.mask_id) a.ids[(int64_t)b * a.n + pos] = win_v;
         a.scores[(int64_t)b * a.n + pos] = 1.0f - pr;
       }
       return;
     }
-    fallback = true;
   }
   // the sampled threshold missed, a list overflowed, or too many winners failed the rank test: this row goes through the materialised path
   // (fallback kernels of this step)
@@ -442,7 +512,7 @@ logits_finish_kernel(const mmg_logits_sample_args a, float tdiv, const LfFinish 
   __syncthreads();
   const int slot = s_slot;
   if (slot < f.fb_cap)
-    for (int i = tid; i < f.K / 8; i += SMP_THREADS)
+    for (int i = tid; i < f.K / 8; i += LFN_THREADS)
       reinterpret_cast<uint4*>(f.e_fb + (int64_t)slot * f.K)[i] = reinterpret_cast<const uint4*>(f.e + r * f.K)[i];
 }
 
@@ -620,14 +690,9 @@ extern "C" int mmg_logits_fused(const mmg_logits_fused_args* a, void* stream) {
     LfFinish f{};
     f.parts = parts; f.lists = lists; f.S = pl.S; f.cap = pl.cap; f.e = reinterpret_cast<const bf16*>(a->e); f.K = a->K;
     f.fb_count = fb_count; f.fb_rows = fb_rows; f.e_fb = e_fb; f.fb_cap = LF_FB_CAP; f.status = a->status;
-    static const size_t smem = (size_t)SMP_CAP * 8;      // padded layouts beyond SMP_CAP entries fall back
-    static cudaError_t at0 = cudaFuncSetAttribute(logits_finish_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    static cudaError_t at1 = cudaFuncSetAttribute(logits_finish_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    static cudaError_t at2 = cudaFuncSetAttribute(logits_finish_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (at0 != cudaSuccess || at1 != cudaSuccess || at2 != cudaSuccess) return fail(MMG_ECUDA, "cudaFuncSetAttribute(logits_finish)");
-    if (s.u) MMG_CUDA(launch_pdl(logits_finish_kernel<1>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, s, t, f));
-    else if (s.rng_mode == 1) MMG_CUDA(launch_pdl(logits_finish_kernel<2>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, s, t, f));
-    else MMG_CUDA(launch_pdl(logits_finish_kernel<0>, dim3((unsigned)R), dim3(SMP_THREADS), smem, st, s, t, f));
+    if (s.u) MMG_CUDA(launch_pdl(logits_finish_kernel<1>, dim3((unsigned)R), dim3(LFN_THREADS), 0, st, s, t, f));
+    else if (s.rng_mode == 1) MMG_CUDA(launch_pdl(logits_finish_kernel<2>, dim3((unsigned)R), dim3(LFN_THREADS), 0, st, s, t, f));
+    else MMG_CUDA(launch_pdl(logits_finish_kernel<0>, dim3((unsigned)R), dim3(LFN_THREADS), 0, st, s, t, f));
     MMG_LAUNCHED();
   }
   {   // 5. fallback rows: materialised logits of at most LF_FB_CAP rows (the kernel exits at once when no row was flagged)

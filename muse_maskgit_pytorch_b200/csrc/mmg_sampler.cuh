@@ -245,77 +245,4 @@ __device__ __forceinline__ void sample_from_list(const mmg_logits_sample_args& a
   }
 }
 
-// The same selection on an interleaved list `lst[s] = (logit bits, vocabulary index)` (the layout the fused logits GEMM writes), keeping NO per-
-// candidate state in registers: one pass computes the perturbed values and each thread keeps only its best; if the block's winner fails the
-// exact-rank test (it lies between the candidate threshold and the true k-th value: the list holds ~ k + 4 sigma entries) its slot joins a small
-// exclusion list and the pass is repeated — the noise is a pure function of (row, vocabulary index), so the repeat reproduces the same values and
-// the result equals sample_from_list's.  Entries with index 0x7fffffff are padding.  Returns false when more than SMP_MAX_EXCL winners in a row
-// failed (the caller sends the row through the materialised path).
-constexpr int SMP_MAX_EXCL = 24;
-template <int MODE>
-__device__ __forceinline__ bool sample_from_pairs(const mmg_logits_sample_args& a, float tdiv, const uint2* lst, int n, int k, int V,
-                                                  int b, int pos, SampleScratch& sc, int* excl, int tid, int warp, int lane, int& win_v, float& win_x) {
-  const int64_t grow = a.row_offset + (int64_t)b * a.n + pos;
-  const uint64_t seed = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
-  const float inv_t = 1.0f / tdiv;
-  uint64_t aq0 = 0, aoff4 = 0; uint32_t ar0 = 0;
-  if (MODE == 2) {
-    const uint64_t base = (uint64_t)grow * (uint64_t)V;
-    aq0 = base / a.aten_stride; ar0 = (uint32_t)(base - aq0 * a.aten_stride);
-    aoff4 = (a.aten_offset + (a.aten_offset_dev ? *a.aten_offset_dev : 0ull)) >> 2;
-  }
-  PhiloxRow prow;
-  if (MODE == 0) prow = philox_row((uint32_t)a.step, (uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
-  win_v = -1; win_x = 0.f;
-  for (int nex = 0; ; ++nex) {
-    float bv = -FLT_MAX; int bi = 0x7fffffff, bs = -1;
-    for (int s = tid; s < n; s += SMP_THREADS) {
-      const uint2 en = lst[s];
-      const int v = (int)en.y;
-      bool skip = v == 0x7fffffff;
-      for (int e = 0; e < nex; ++e) skip |= excl[e] == s;
-      if (skip) continue;
-      const float x = __uint_as_float(en.x);
-      float p;
-      if (MODE != 0) {
-        float u;
-        if (MODE == 1) u = a.u[((int64_t)b * a.n + pos) * V + v];
-        else { const uint32_t r = ar0 + (uint32_t)v, dq = r / a.aten_stride; u = aten_uniform(r - dq * a.aten_stride, aq0 + dq, aoff4, seed); }
-        const float l1 = logf(fmaxf(u, 1e-20f));
-        p = __fdiv_rn(x, tdiv) - logf(fmaxf(-l1, 1e-20f));
-      } else {
-        const float u = (float)(philox_first_row((uint32_t)v, prow) >> 8) * (1.0f / 16777216.0f);
-        const float l1 = __logf(fmaxf(u, 1e-20f));
-        p = fmaf(x, inv_t, -__logf(fmaxf(-l1, 1e-20f)));
-      }
-      if (bs < 0 || better(p, v, bv, bi)) { bv = p; bi = v; bs = s; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o); const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-      if (os >= 0 && (bs < 0 || better(ov, oi, bv, bi))) { bv = ov; bi = oi; bs = os; }
-    }
-    __syncthreads();
-    if (lane == 0) { sc.redf[warp] = bv; sc.redi[warp] = bi; sc.redj[warp] = bs; }
-    __syncthreads();
-    bv = sc.redf[0]; bi = sc.redi[0]; bs = sc.redj[0];
-#pragma unroll
-    for (int w = 1; w < SMP_THREADS / 32; ++w) {
-      const float ov = sc.redf[w]; const int oi = sc.redi[w], os = sc.redj[w];
-      if (os >= 0 && (bs < 0 || better(ov, oi, bv, bi))) { bv = ov; bi = oi; bs = os; }
-    }
-    if (bs < 0) return true;                                  // nothing left (degenerate row): win_v stays -1
-    // exact rank of the candidate inside the row (the list covers everything >= its value; padding entries hold -FLT_MAX / 0x7fffffff)
-    const float cx = __uint_as_float(lst[bs].x);
-    int c = 0;
-    for (int s = tid; s < n; s += SMP_THREADS) { const uint2 en = lst[s]; const float x = __uint_as_float(en.x); c += (x > cx) || (x == cx && (int)en.y < bi); }
-    int rank, dummy;
-    block_sum2(c, 0, sc.red, warp, lane, rank, dummy);
-    if (rank < k) { win_v = bi; win_x = cx; return true; }
-    if (nex == SMP_MAX_EXCL) return false;
-    if (tid == 0) excl[nex] = bs;
-    __syncthreads();
-  }
-}
-
 }  // namespace mmg

@@ -23,7 +23,7 @@ StepWs carve(int32_t b, int32_t branches, int32_t n, int32_t dim, int32_t heads,
   w.v = o;      o += up256(BH * tk * 64 * 2);
   w.ao = o;     o += up256(R * inner * 2);
   w.h = o;      o += up256(R * (uint64_t)Fp * 2);
-  w.stats = o;  o += up256(R * 2 * 4);
+  w.stats = o;  o += up256(R * (uint64_t)(Fp / 32) * 2 * 4);
   w.e = o;      o += up256((uint64_t)b * n * dim * 2);
   w.logits = o; o += up256((uint64_t)b * max_masked * V * 4);
   w.total = o;
@@ -42,21 +42,21 @@ extern "C" int mmg_ff_geglu(const mmg_ff_geglu_args* a, void* stream) {
   MMG_CHECK_ARG(a->rows >= 0 && a->dim > 0 && a->F > 0 && a->Fp >= a->F && a->Fp % 64 == 0 && a->dim % 64 == 0, "mmg_ff_geglu: dim=%d F=%d Fp=%d", a->dim, a->F, a->Fp);
   if (a->rows == 0) return MMG_OK;
   int rc;
-  {   // xn = LN(x [+ add]) * gamma; the GEGLU row statistics are reset in the same pass
+  {   // xn = LN(x [+ add]) * gamma
     mmg_layernorm_args ln{};
     ln.x = a->x; ln.x_dtype = MMG_F32; ln.y = a->xn; ln.y_dtype = MMG_BF16; ln.gamma = a->ln_gamma;
-    ln.add = a->add; ln.x_out = a->add ? a->x : nullptr; ln.add_from = a->add ? a->add_from : 0; ln.zero_stats = a->stats;
+    ln.add = a->add; ln.x_out = a->add ? a->x : nullptr; ln.add_from = a->add ? a->add_from : 0;
     ln.rows = a->rows; ln.width = a->dim; ln.ldx = a->dim; ln.ldy = a->dim;
     if ((rc = mmg_layernorm(&ln, stream))) return rc;
   }
-  {   // h = gate * gelu(x), per-row (sum, sumsq) of h accumulated by the epilogue
+  {   // h = gate * gelu(x); the epilogue writes the (sum, sumsq) of every 32-output chunk of h to its own slot
     mmg_epilogue_args e{};
-    e.out = a->h; e.ldo = a->Fp; e.out_dtype = MMG_BF16; e.row_stats = a->stats;
+    e.out = a->h; e.ldo = a->Fp; e.out_dtype = MMG_BF16; e.row_stats = a->stats; e.stats_slots = a->Fp / 32;
     if ((rc = linear_bf16(a->xn, a->w1, a->rows, 2 * (int64_t)a->Fp, a->dim, MMG_EPI_GEGLU, e, stream))) return rc;
   }
   {   // x += LN(h) * gamma_inner W2^T, LayerNorm folded through the product
     mmg_epilogue_args e{};
-    e.out = a->x; e.ldo = a->dim; e.out_dtype = MMG_F32; e.resid = a->x; e.ldr = a->dim; e.bias = a->cvec; e.row_stats = a->stats; e.ln_width = a->F;
+    e.out = a->x; e.ldo = a->dim; e.out_dtype = MMG_F32; e.resid = a->x; e.ldr = a->dim; e.bias = a->cvec; e.row_stats = a->stats; e.stats_slots = a->Fp / 32; e.ln_width = a->F;
     if ((rc = linear_bf16(a->h, a->w2f, a->rows, a->dim, a->Fp, MMG_EPI_LNFOLD_RESIDUAL, e, stream))) return rc;
   }
   return MMG_OK;

@@ -243,7 +243,7 @@ class Transformer(nn.Module):
                   ao=torch.empty((R, inner), device=dev, dtype=adt),
                   h=torch.empty((R, Fp), device=dev, dtype=adt),
                   hn=torch.empty((R, Fp), device=dev, dtype=adt),
-                  stats=torch.zeros((R, 2), device=dev, dtype=torch.float32))
+                  stats=torch.zeros((R, Fp // 32, 2), device=dev, dtype=torch.float32))   # per-chunk (sum, sumsq) of the GEGLU output
         if len(cache) >= 4:
             cache.pop(next(iter(cache)))
         cache[key] = ws
@@ -299,17 +299,16 @@ class Transformer(nn.Module):
             # --- feed forward (the constant null-branch cross-attention term is folded into this LayerNorm) ---
             if pending_add and sorted(pending_add) == list(range(min(pending_add), nb)):
                 # one launch for all branches: rows of the all-masked (null) branches get += to_out(null_v) before the norm
-                ops.layernorm(x, ff["g0"], xn, add=ca["null_out"], x_out=x, zero_stats=ws["stats"], add_from=min(pending_add) * bn)
+                ops.layernorm(x, ff["g0"], xn, add=ca["null_out"], x_out=x, add_from=min(pending_add) * bn)
             elif not pending_add:
-                ops.layernorm(x, ff["g0"], xn, zero_stats=ws["stats"])
+                ops.layernorm(x, ff["g0"], xn)
             else:
                 for j in range(nb):
                     xs = x[j * bn:(j + 1) * bn]
-                    zs = ws["stats"][j * bn:(j + 1) * bn]      # row statistics of the GEGLU output, reset here, accumulated by FF1's epilogue
                     if j in pending_add:
-                        ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn], add=pending_add[j], x_out=xs, zero_stats=zs)
+                        ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn], add=pending_add[j], x_out=xs)
                     else:
-                        ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn], zero_stats=zs)
+                        ops.layernorm(xs, ff["g0"], xn[j * bn:(j + 1) * bn])
             self._ff_tail(xn, ff, x, ws, R)
         return x
 
@@ -329,7 +328,7 @@ class Transformer(nn.Module):
             ops.linear(xn, sa["wqkv"], None, epilogue=ops.EPI_QKV, epi=epi)
             ops.attention(q, k, v, ao, nb * b, heads, n + 1, logit_bound=sa["bound"])
             # x += attn out; live rows: xn = LN(x)*g_cross; rows >= Rl: x += to_out(null_v), xn = LN(x)*g_ff; FF row statistics reset
-            ops.linear(ao, sa["wo"], x, epilogue=ops.EPI_RESIDUAL, resid=x, row_stats=stats, ln_out=xn,
+            ops.linear(ao, sa["wo"], x, epilogue=ops.EPI_RESIDUAL, resid=x, ln_out=xn,
                        ln_gamma=ca["g"] if Rl > 0 else ff["g0"], ln_gamma_b=ff["g0"], ln_add=ca["null_out"], ln_split=Rl)
             if Rl > 0:
                 kc, vc = ctx["kv"][li]
@@ -342,20 +341,23 @@ class Transformer(nn.Module):
             h = ws["h"][:R, :ff["Fp"]]
             if ff["Fp"] != ws["h"].shape[1]:
                 h = h.contiguous()
+            stats = ws["stats"][:R, :ff["Fp"] // 32]
+            if stats.shape[1] != ws["stats"].shape[1]:
+                stats = stats.contiguous()
             ops.linear(xn, ff["w1"], h, epilogue=ops.EPI_GEGLU, row_stats=stats)
             nxt = layers[li + 1]["sa"]["g"] if li + 1 < len(layers) else None
             ops.linear(h, ff["w2f"], x, epilogue=ops.EPI_LNFOLD_RESIDUAL, bias=ff["cvec"], resid=x, row_stats=stats, ln_width=ff["F"],
                        ln_out=xn if nxt is not None else None, ln_gamma=nxt)
         return x
 
-    def _ff_tail(self, xn, ff, x, ws, R, stats_zeroed=True):
+    def _ff_tail(self, xn, ff, x, ws, R):
         h, hn = ws["h"][:R, :ff["Fp"]], ws["hn"][:R, :ff["Fp"]]
         if ff["Fp"] != ws["h"].shape[1]:
             h, hn = h.contiguous(), hn.contiguous()
         if "w2f" in ff:      # bf16: inner LayerNorm folded into the two GEMM epilogues (no pass over h between them)
-            stats = ws["stats"][:R]
-            if not stats_zeroed:
-                stats.zero_()
+            stats = ws["stats"][:R, :ff["Fp"] // 32]     # per-chunk (sum, sumsq) partials written by FF1's epilogue, added in order by FF2's
+            if stats.shape[1] != ws["stats"].shape[1]:
+                stats = stats.contiguous()
             ops.linear(xn[:R], ff["w1"], h, epilogue=ops.EPI_GEGLU, row_stats=stats)
             ops.linear(h, ff["w2f"], x[:R], epilogue=ops.EPI_LNFOLD_RESIDUAL, bias=ff["cvec"], resid=x[:R], row_stats=stats, ln_width=ff["F"])
             return
@@ -366,7 +368,7 @@ class Transformer(nn.Module):
     def _ff(self, inp, ff, x_acc, ws, R):
         """x_acc += FeedForward(inp)   (self-conditioning embed, muse_maskgit_pytorch.py:325-328)"""
         xn = ws["xn"][:R]
-        ops.layernorm(inp, ff["g0"], xn, zero_stats=ws["stats"][:R])
+        ops.layernorm(inp, ff["g0"], xn)
         self._ff_tail(xn, ff, x_acc, ws, R)
 
     # ----- public API ---------------------------------------------------------------------------------------------------

@@ -17,6 +17,8 @@ def _chk(t, name="tensor"):
 def _epi(out=None, ldo=0, bias=None, act=0, resid=None, ldr=0, row_stats=None, ln_width=0):
     e = L.EpilogueArgs()
     e.row_stats = L.ptr(row_stats); e.ln_width = ln_width
+    if row_stats is not None:                     # [M, slots, 2] per-chunk partials (GEGLU writes, LNFOLD reads); [M, 2] = one slot of totals
+        e.stats_slots = row_stats.shape[1] if row_stats.dim() == 3 else 1
     if out is not None:
         e.out = out.data_ptr(); e.ldo = ldo
         e.out_dtype = L.dt(out) if out.dtype in (torch.float32, torch.bfloat16) else L.F32     # int64 outputs (LFQ ids / argmin keys)
@@ -272,6 +274,7 @@ def ff_geglu(x, ln_gamma, w1, w2f, cvec, F, xn, h, stats, add=None, add_from=0):
     a.x = _chk(x).data_ptr(); a.rows, a.dim = x.shape; a.F = F; a.Fp = w2f.shape[1]
     a.ln_gamma = ln_gamma.data_ptr(); a.w1 = _chk(w1).data_ptr(); a.w2f = _chk(w2f).data_ptr(); a.cvec = cvec.data_ptr()
     a.add = L.ptr(add); a.add_from = add_from
+    assert stats.dtype == torch.float32 and stats.numel() >= a.rows * (a.Fp // 32) * 2, "stats: [rows, Fp / 32, 2] fp32 per-chunk partials"
     a.xn = _chk(xn).data_ptr(); a.h = _chk(h).data_ptr(); a.stats = stats.data_ptr()
     assert x.dtype == torch.float32 and w1.dtype == torch.bfloat16 and w1.shape[0] == 2 * a.Fp and tuple(h.shape) == (a.rows, a.Fp)
     L.call("mmg_ff_geglu", a)

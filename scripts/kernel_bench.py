@@ -64,9 +64,9 @@ if want("gemm"):
         elif epi == "resid":
             out = torch.zeros((M, N), device="cuda"); fn = lambda: ops.linear(a, w, out, epilogue=ops.EPI_RESIDUAL, resid=out)
         elif epi == "geglu_stats":
-            out = torch.empty((M, N // 2), device="cuda", dtype=bf); st = torch.zeros((M, 2), device="cuda"); fn = lambda: ops.linear(a, w, out, epilogue=ops.EPI_GEGLU, row_stats=st)
+            out = torch.empty((M, N // 2), device="cuda", dtype=bf); st = torch.zeros((M, N // 64, 2), device="cuda"); fn = lambda: ops.linear(a, w, out, epilogue=ops.EPI_GEGLU, row_stats=st)
         elif epi == "lnfold":
-            out = torch.zeros((M, N), device="cuda"); st = torch.ones((M, 2), device="cuda") * 1365; cv = torch.zeros(N, device="cuda")
+            out = torch.zeros((M, N), device="cuda"); st = torch.ones((M, K // 32, 2), device="cuda") * 31; cv = torch.zeros(N, device="cuda")
             fn = lambda: ops.linear(a, w, out, epilogue=ops.EPI_LNFOLD_RESIDUAL, bias=cv, resid=out, row_stats=st, ln_width=1365)
         else:
             out = torch.empty((M, N // 2), device="cuda", dtype=bf); e = ops._epi(out, N // 2); fn = lambda: ops.linear(a, w, None, epilogue=ops.EPI_GEGLU, epi=e)

@@ -446,12 +446,15 @@ def test_linear_geglu_lnfold_pair():
     cvec = w2f.float().sum(1)
     x = rnd("x", (M, dim))
     h = torch.empty((M, Fp), device="cuda", dtype=bf)
-    stats = torch.zeros((M, 2), device="cuda")
+    stats = torch.full((M, Fp // 32, 2), float("nan"), device="cuda")      # per-chunk partials: every slot is written, none accumulated
     xd = dev(x)
     ops().linear(dev(a, bf), dev(w1, bf), h, epilogue=ops().EPI_GEGLU, row_stats=stats)
     ops().linear(h, dev(w2f), xd, epilogue=ops().EPI_LNFOLD_RESIDUAL, bias=dev(cvec), resid=xd, row_stats=stats, ln_width=Fu)
     href = (a @ wg.t()) * F.gelu(a @ wx.t())
-    ok, msg = close(stats[:, 0], href.sum(-1), 2e-3, 1e-3)
+    # the statistics are those of the bf16-rounded outputs, chunk by chunk
+    hq = h.float().cpu().view(M, Fp // 32, 32)
+    assert torch.allclose(stats[..., 0].cpu(), hq.sum(-1), atol=1e-4, rtol=1e-5) and torch.allclose(stats[..., 1].cpu(), (hq * hq).sum(-1), atol=1e-4, rtol=1e-5)
+    ok, msg = close(stats[..., 0].sum(-1), href.sum(-1), 5e-3 * float(href.sum(-1).abs().max()), 1e-2)     # bf16 rounding of 341 summands
     assert ok, "row sums: " + msg
     ref = x + F.layer_norm(href, (Fu,), g3, None) @ w2.t()
     ok, msg = close(xd, ref, 3e-2, 1e-2)
@@ -505,18 +508,41 @@ def test_logits_sample_philox_matches_oracle_stream():
     assert (got == pred).float().mean() > 0.9
 
 
+def test_ff_geglu_lnfold_bitwise_reproducible_at_block_width():
+    """dim 512 / inner 1365 (44 statistic chunks per row, 11 column tiles, CTA pairs): the folded-LayerNorm FeedForward gives the same bits on
+    every run — the row statistics are per-chunk partials added in a fixed order, not atomics."""
+    M, K, Fu, Fp, dim = 4096, 512, 1365, 1408, 512
+    bf = torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn((M, K), device="cuda", generator=g).to(bf)
+    w1 = (torch.randn((2 * Fp, K), device="cuda", generator=g) * K ** -0.5).to(bf)
+    w2f = (torch.randn((dim, Fp), device="cuda", generator=g) * Fu ** -0.5).to(bf); w2f[:, Fu:] = 0
+    cvec = w2f.float().sum(1).contiguous()
+    x0 = torch.randn((M, dim), device="cuda", generator=g)
+    outs = []
+    for _ in range(4):
+        h = torch.empty((M, Fp), device="cuda", dtype=bf); stats = torch.empty((M, Fp // 32, 2), device="cuda"); xd = x0.clone()
+        ops().linear(a, w1, h, epilogue=ops().EPI_GEGLU, row_stats=stats)
+        ops().linear(h, w2f, xd, epilogue=ops().EPI_LNFOLD_RESIDUAL, bias=cvec, resid=xd, row_stats=stats, ln_width=Fu)
+        outs.append((h.clone(), stats.clone(), xd))
+    for h, st, xd in outs[1:]:
+        assert torch.equal(h, outs[0][0]) and torch.equal(st, outs[0][1])
+        # the in-place residual is a TMA reduction (fp32 adds in L2, one per element): also order-independent
+        assert torch.equal(xd, outs[0][2])
+
+
 @pytest.mark.parametrize("N", [512, 128])
 def test_linear_residual_with_fused_layernorm(N):
     """cluster-of-2 GEMM: x += a W^T (rows >= split also += add), ln_out = LN(x) * gamma (gamma_b for rows >= split),
-    row statistics buffer reset.  The two CTAs exchange (sum, sumsq) through distributed shared memory."""
+    The two CTAs exchange (sum, sumsq) through distributed shared memory."""
     M, K, split = 700, 256, 384
     bf = torch.bfloat16
     a, w = rnd("a", (M, K), bf), rnd("w", (N, K), bf, std=K ** -0.5)
     x = rnd("x", (M, N)) * 2 + 0.3
     ga, gb, add = 1 + 0.1 * rnd("ga", (N,)), 1 + 0.1 * rnd("gb", (N,)), rnd("add", (N,))
-    xd = dev(x); xn = torch.zeros((M, N), device="cuda", dtype=bf); stats = torch.ones((M, 2), device="cuda")
+    xd = dev(x); xn = torch.zeros((M, N), device="cuda", dtype=bf)
     gad, gbd, addd = dev(ga), dev(gb), dev(add)
-    ops().linear(dev(a, bf), dev(w, bf), xd, epilogue=ops().EPI_RESIDUAL, resid=xd, row_stats=stats, ln_out=xn, ln_gamma=gad, ln_gamma_b=gbd, ln_add=addd, ln_split=split)
+    ops().linear(dev(a, bf), dev(w, bf), xd, epilogue=ops().EPI_RESIDUAL, resid=xd, ln_out=xn, ln_gamma=gad, ln_gamma_b=gbd, ln_add=addd, ln_split=split)
     ref = x + a @ w.t()
     ref[split:] += add
     ok, msg = close(xd, ref, 3e-4)
@@ -524,7 +550,6 @@ def test_linear_residual_with_fused_layernorm(N):
     lref = torch.cat((F.layer_norm(ref[:split], (N,), ga, None), F.layer_norm(ref[split:], (N,), gb, None)))
     ok, msg = close(xn, lref, 2e-2, 1e-2)
     assert ok, "ln_out: " + msg
-    assert float(stats.abs().max()) == 0.
 
 
 @pytest.mark.parametrize("cfg_branch", [False, True])

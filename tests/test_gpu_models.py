@@ -382,7 +382,7 @@ def test_ff_geglu_c_abi_vs_torch():
     w1p[dst[ok]] = w1[:F_]; w1p[dst[ok] + 32] = w1[F_:]
     xd = x.cuda()
     ops.ff_geglu(xd, g0.cuda(), w1p.to(bf).cuda(), w2f_b.cuda(), w2f_b.float().sum(1).cuda(), F_,
-                 torch.empty(R, dim, dtype=bf, device="cuda"), torch.empty(R, Fp, dtype=bf, device="cuda"), torch.zeros(R, 2, device="cuda"),
+                 torch.empty(R, dim, dtype=bf, device="cuda"), torch.empty(R, Fp, dtype=bf, device="cuda"), torch.empty(R, Fp // 32, 2, device="cuda"),
                  add=add.cuda(), add_from=split)
     err = (xd.cpu() - want).abs().max().item()
     assert err < 3e-2, err
