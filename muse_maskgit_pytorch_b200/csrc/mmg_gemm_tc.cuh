@@ -280,20 +280,15 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       if (tr) MMG_TR(5, MMG_CLK());
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       bool released = false;
-#pragma unroll 1
-      for (int c = c_first; c < c_end; c += c_step) {
-        if (!mine) break;
-        float v[64];
-        tmem_ld_32x32b_x32(t_row + c * 64, v);
-        tmem_ld_32x32b_x32(t_row + c * 64 + 32, v + 32);
-        tmem_ld_wait();
-        if (c + c_step >= c_end) {                 // last chunk is in registers: hand the accumulator stage back before the math
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { if (PAIR) mbar_arrive_remote(tmem_empty0 + (uint32_t)acc * 8u); else mbar_arrive(tmem_empty + acc); }
-          if (tr) MMG_TR(6, MMG_CLK());
-          released = true;
-        }
+      auto release = [&]() {                       // hand the accumulator stage back to the MMA issuer (all of this warp's chunks are in registers)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) mbar_arrive_remote(tmem_empty0 + (uint32_t)acc * 8u); else mbar_arrive(tmem_empty + acc); }
+        if (tr) MMG_TR(6, MMG_CLK());
+        released = true;
+      };
+      // the epilogue of one 64-column accumulator chunk held in v
+      auto chunk = [&](const int c, float (&v)[64]) {
         const int col0 = n_blk * BN + c * 64;
         if (GEGLUT) {
           // columns past N are zero accumulators (TMA zero-fills the missing W rows) and are clipped by the tensor map, rows past M too
@@ -368,6 +363,34 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
           } else {
             epi.template apply<true>(row, col0, v, 64);
           }
+        }
+      };
+      if constexpr ((QKVT || GEGLUT) && BN == 256) {
+        // two chunks per warp and an epilogue that needs no residual registers: BOTH chunks leave TMEM first (128 registers) and the stage goes
+        // back ~700 cycles after tmem_full instead of after the first chunk's arithmetic and store (QKV: 2 550 cycles, during which the MMA
+        // issuer sat waiting for the stage, scripts/trace_gemm.py)
+        if (mine) {
+          float va[64], vb[64];
+          const int ca = c_first, cb = c_first + c_step;
+          tmem_ld_32x32b_x32(t_row + ca * 64, va);
+          tmem_ld_32x32b_x32(t_row + ca * 64 + 32, va + 32);
+          tmem_ld_32x32b_x32(t_row + cb * 64, vb);
+          tmem_ld_32x32b_x32(t_row + cb * 64 + 32, vb + 32);
+          tmem_ld_wait();
+          release();
+          chunk(ca, va);
+          chunk(cb, vb);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = c_first; c < c_end; c += c_step) {
+          if (!mine) break;
+          float v[64];
+          tmem_ld_32x32b_x32(t_row + c * 64, v);
+          tmem_ld_32x32b_x32(t_row + c * 64 + 32, v + 32);
+          tmem_ld_wait();
+          if (c + c_step >= c_end) release();        // last chunk is in registers: hand the accumulator stage back before the math
+          chunk(c, v);
         }
       }
       if (valid && mine) epi.end_row(row);

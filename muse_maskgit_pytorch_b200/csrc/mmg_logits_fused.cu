@@ -380,8 +380,11 @@ __device__ __forceinline__ void lfn_for_each(const uint2* __restrict__ row_lists
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(LFN_THREADS, 6)
+// MINB = CTAs per SM the register budget is sized for: 6 (39 registers: the Philox round keys are re-derived per candidate) or 4 (64 registers,
+// keys kept).  The kernel is issue-bound (ncu: 71 % issue slots, ALU pipe 53 %), so fewer instructions beat more resident warps; MMG_FINISH_MINB=6
+// selects the other build.
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(LFN_THREADS, MINB)
 logits_finish_kernel(const mmg_logits_sample_args a, float tdiv, const LfFinish f) {
   __shared__ int s_cnt[LF_SEGS * LF_MAX_SPLITS];
   __shared__ float s_m[LF_SEGS * LF_MAX_SPLITS], s_s[LF_SEGS * LF_MAX_SPLITS];
@@ -690,9 +693,11 @@ extern "C" int mmg_logits_fused(const mmg_logits_fused_args* a, void* stream) {
     LfFinish f{};
     f.parts = parts; f.lists = lists; f.S = pl.S; f.cap = pl.cap; f.e = reinterpret_cast<const bf16*>(a->e); f.K = a->K;
     f.fb_count = fb_count; f.fb_rows = fb_rows; f.e_fb = e_fb; f.fb_cap = LF_FB_CAP; f.status = a->status;
-    if (s.u) MMG_CUDA(launch_pdl(logits_finish_kernel<1>, dim3((unsigned)R), dim3(LFN_THREADS), 0, st, s, t, f));
-    else if (s.rng_mode == 1) MMG_CUDA(launch_pdl(logits_finish_kernel<2>, dim3((unsigned)R), dim3(LFN_THREADS), 0, st, s, t, f));
-    else MMG_CUDA(launch_pdl(logits_finish_kernel<0>, dim3((unsigned)R), dim3(LFN_THREADS), 0, st, s, t, f));
+    static const int minb = [] { const char* e = getenv("MMG_FINISH_MINB"); return e ? atoi(e) : 4; }();
+    if (s.u) MMG_CUDA(launch_pdl(logits_finish_kernel<1, 4>, dim3((unsigned)R), dim3(LFN_THREADS), 0, st, s, t, f));
+    else if (s.rng_mode == 1) MMG_CUDA(launch_pdl(logits_finish_kernel<2, 4>, dim3((unsigned)R), dim3(LFN_THREADS), 0, st, s, t, f));
+    else if (minb == 6) MMG_CUDA(launch_pdl(logits_finish_kernel<0, 6>, dim3((unsigned)R), dim3(LFN_THREADS), 0, st, s, t, f));
+    else MMG_CUDA(launch_pdl(logits_finish_kernel<0, 4>, dim3((unsigned)R), dim3(LFN_THREADS), 0, st, s, t, f));
     MMG_LAUNCHED();
   }
   {   // 5. fallback rows: materialised logits of at most LF_FB_CAP rows (the kernel exits at once when no row was flagged)

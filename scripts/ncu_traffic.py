@@ -37,6 +37,14 @@ n = sum(a[0] for a in gemm)
 out = {"tc_gemm_dram_bytes_per_launch": round(sum(a[2] + a[3] for a in gemm) / max(n, 1)), "tc_gemm_launches": n,
        "tc_gemm_dram_read_gb": round(sum(a[2] for a in gemm) / 1e9, 3), "tc_gemm_dram_write_gb": round(sum(a[3] for a in gemm) / 1e9, 3),
        "source": f"{sys.argv[1].split('/')[-1]}: ncu dram__bytes_read.sum + dram__bytes_write.sum over the tcgen05 GEMM launches of one eager generate() (batch 64), per launch"}
+# share of the fused logits + sampling entry point (mmg_logits_fused) that is tcgen05 GEMM time: its logits GEMM and the 4096-column sample GEMM
+# (the only fp32 TMA-store GEMM of a bf16 generate()) against the threshold / finisher / fallback-sampler kernels of the same call
+tsum = lambda pred: sum(a[1] for k, a in agg.items() if pred(k))
+fused_gemm = tsum(lambda k: k.startswith("tc_logits_kernel") or k.startswith("tc_gemm_kernel<256, 0, 1, 3>") or k.startswith("tc_gemm_kernel<256, 0, 0, 3>"))
+fused_other = tsum(lambda k: k.startswith("logits_finish_kernel") or k.startswith("logits_threshold") or k.startswith("logits_sample"))
+if fused_gemm > 0:
+    out["logits_fused_gemm_share"] = round(fused_gemm / (fused_gemm + fused_other), 4)
+    out["logits_fused_note"] = "ncu time of tc_logits_kernel + the sample GEMM / (those + logits_threshold + logits_finish + fallback sampler) in the same launch list"
 if len(sys.argv) > 2:
     json.dump(out, open(sys.argv[2], "w"), indent=1)
 print(json.dumps(out))
