@@ -101,7 +101,10 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   static_assert(!GEGLUT || BN == 256, "the GEGLU tile epilogue pairs adjacent 64-column chunks of a 256-column tile");
   static_assert(!(LNF && PAIR), "LayerNorm fusion and CTA pairs both claim the cluster");
   static_assert(!(LNF && EPI_MODE != 0), "the LayerNorm-fused kernel has no room for the epilogue tiles");
-  constexpr int STAGES = PAIR ? Cfg::PAIR_STAGES : Cfg::STAGES;
+  // QKV tile epilogue in pair mode: TWO 4 KB tiles per warp (a warp issues two TMA stores per output tile; with one tile the second chunk
+  // waited ~1 500 cycles for the first store's shared-memory read, queued behind the operand loads in the TMA unit) paid for with one ring stage
+  constexpr int EPI_BUFS = (QKVT && PAIR && BN == 256) ? 2 : 1;
+  constexpr int STAGES = PAIR ? (EPI_BUFS == 2 ? Cfg::PAIR_STAGES - 1 : Cfg::PAIR_STAGES) : Cfg::STAGES;
   constexpr int STAGE_BYTES = PAIR ? Cfg::PAIR_STAGE_BYTES : Cfg::STAGE_BYTES;
 
   if (p.skip_if_zero) { pdl_wait(); if (*p.skip_if_zero == 0) return; }       // uniform over the grid: nothing has been set up yet
@@ -310,12 +313,13 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         } else if (QKVT && col0 < p.N) {
           int h;
           const int which = epi.template qkv_chunk<true>(col0, v, h);
-          const uint32_t wtile = smem_u32(smem + STAGES * STAGE_BYTES + 1024) + (uint32_t)(warp - 4) * 4096u;
+          const uint32_t wtile = smem_u32(smem + STAGES * STAGE_BYTES + 1024) + (uint32_t)(warp - 4) * (4096u * EPI_BUFS) +
+                                 (EPI_BUFS == 2 ? (uint32_t)((c - c_first) / c_step) * 4096u : 0u);
           const uint32_t rw = (uint32_t)(m_blk * TC_BM + quarter * 32), tok = (uint32_t)epi.p.tokens;
           const uint32_t bq = rw / tok, t0 = rw - bq * tok;                       // warp-uniform: the 32 rows are tokens t0 .. t0+31 of sequence bq
           const int64_t drow = which == 0 ? ((int64_t)bq * epi.p.heads + h) * epi.p.q_rows + t0
                                           : ((int64_t)bq * epi.p.heads + h) * epi.p.kv_rows + epi.p.key_off + t0;
-          if (lane == 0) bulk_wait_read0();               // this warp's previous store has left the tile
+          if (lane == 0) { if (EPI_BUFS == 2) bulk_wait_read1(); else bulk_wait_read0(); }      // the store that last used this tile has read it
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)

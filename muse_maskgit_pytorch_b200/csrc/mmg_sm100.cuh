@@ -99,6 +99,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t ssrc
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources reusable
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // all but the newest group
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }             // fully complete
 
 // CTA-pair (cta_group::2) variants: the load lands in THIS CTA's shared memory, its bytes are counted on the LEADER CTA's
