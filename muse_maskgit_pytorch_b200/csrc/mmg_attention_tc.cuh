@@ -160,14 +160,19 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
           tmem_ld_32x32b_x32(tS + lane_base + c, s);
           tmem_ld_wait();
           const int j0 = blk * KB + c;
+          // liveness of the 32 keys of this chunk as one ballot word (lane l tests key j0 + l: ONE coalesced mask byte per lane instead of 32
+          // byte loads per thread; key 0, the null key, is never masked)
+          uint32_t livew = 0xffffffffu;
+          if (km || j0 + 32 > p.Tk) {
+            const int jl = j0 + lane;
+            livew = __ballot_sync(0xffffffffu, jl < p.Tk && (jl == 0 || !km || km[jl - 1]));
+          }
           if (pass == 0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const int j = j0 + i;
               // masked keys take the value -FLT_MAX in the reference; they only matter for the max if every key is masked,
-              // which cannot happen (key 0, the null key, is never masked)
-              const bool live = j < p.Tk && (j == 0 || !km || km[j - 1]);
-              if (live) row_max = fmaxf(row_max, s[i]);
+              // which cannot happen
+              if ((livew >> i) & 1u) row_max = fmaxf(row_max, s[i]);
             }
           } else {
             uint32_t packed[16];
@@ -176,25 +181,23 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
                 const float p0 = ex2_fast(fmaf(s[i], p.scale_log2e, -mneg)), p1 = ex2_fast(fmaf(s[i + 1], p.scale_log2e, -mneg));
-                __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-                packed[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
-                const float2 pr = __bfloat1622float2(t);
-                row_sum += pr.x + pr.y;
+                packed[i >> 1] = pack_bf16(p0, p1);
+                // denominator from the unrounded weights: the bf16 rounding of P is unbiased, so sum(p~ v) / sum(p) differs from the exactly
+                // normalised sum(p~ v) / sum(p~) by ~2^-9 / sqrt(keys) relative, far below the bf16 rounding of the output (and saves the
+                // unpack + add pair per element in this issue-limited loop)
+                row_sum += p0 + p1;
               }
             } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               float pv[2];
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int j = j0 + i + e;
-                const bool live = j < p.Tk && (j == 0 || !km || km[j - 1]);
-                pv[e] = live ? ex2_fast(fmaf(s[i + e], p.scale_log2e, -mneg)) : 0.f;
-              }
+              for (int e = 0; e < 2; ++e)
+                pv[e] = ((livew >> (i + e)) & 1u) ? ex2_fast(fmaf(s[i + e], p.scale_log2e, -mneg)) : 0.f;
               __nv_bfloat162 t = __floats2bfloat162_rn(pv[0], pv[1]);
               packed[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
-              const float2 pr = __bfloat1622float2(t);     // normalise by the sum of the ROUNDED weights: O = sum(p~ v) / sum(p~)
-              row_sum += pr.x + pr.y;
+              const float2 pr = __bfloat1622float2(t);     // masked / ragged chunks (few live keys, no averaging): normalise by the sum of the
+              row_sum += pr.x + pr.y;                      // ROUNDED weights, O = sum(p~ v) / sum(p~): a row whose only live key is the null key gets exactly null_v
             }
             }
             // P[r, c .. c+31] -> sub-tile (c / 64), 16-byte chunks (c % 64) / 8 .. +3, 128B swizzle: chunk ^= (r & 7)
