@@ -88,7 +88,8 @@ static int attn_launch_cols(const AttnTcParams& p, dim3 grid, size_t smem, cudaS
 
 int attention_tc_launch(const mmg_attention_args* a, cudaStream_t st) {
   AttnTcParams p{};
-  attn_blocks(a->Tk, &p.nb, &p.KB, &p.KB_tail);
+  attn_blocks(a->Tk - 1, &p.nb, &p.KB, &p.KB_tail);         // blocks over the real keys 1 .. Tk-1; the null key (row 0) is handled by the softmax warps
+  p.k = (const bf16*)a->k; p.v = (const bf16*)a->v;
   p.key_mask = a->key_mask; p.out = (bf16*)a->out; p.heads = a->heads; p.Tq = a->Tq; p.Tk = a->Tk; p.Tk_alloc = a->Tk_alloc;
   p.kv_shared = a->kv_batch_stride_zero; p.ldo = a->ldo; p.scale_log2e = a->scale * 1.4426950408889634f;
   // single-pass softmax when the caller bounds |q.k| and exp2((s - bound) * scale * log2e) cannot underflow the fp32 range

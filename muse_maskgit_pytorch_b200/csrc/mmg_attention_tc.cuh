@@ -1,6 +1,9 @@
 // tcgen05 attention for dh = 64 (bf16 operands, fp32 softmax statistics).
 //
-// One CTA = one (batch, head, 128-query tile).  Keys are walked in nb blocks of KB (<= 256, multiple of 32) keys (the last block
+// One CTA = one (batch, head, 128-query tile).  Key 0 of every (batch, head) is the learned null key: it is never masked, and it is handled
+// OUTSIDE the tensor-core blocks — each softmax thread computes its row's q . k_null with 64 FMAs, its weight joins the row sum and
+// p_null * v_null is added to O in the epilogue — so that the n = 256 (1 024, 32) real keys are exactly 4 (8, 1) blocks instead of 4 + a block
+// that holds one key.  The real keys 1 .. Tk-1 are walked in nb blocks of KB (<= 256, multiple of 32) keys (the last block
 // may be shorter: KB_tail), twice (or once, see single_pass):
 //   pass A:  S = Q K^T (tcgen05.mma, M=128, N=KB, 4 k-steps) -> TMEM -> per-row running max        (no P, no V traffic)
 //   pass B:  S again -> p = exp2((s - max) * scale*log2e) in registers (masked / out-of-range keys -> 0), row sums in fp32,
@@ -22,7 +25,8 @@ struct alignas(64) AttnTcParams {
   CUtensorMap tma_q, tma_k, tma_v;
   const uint8_t* key_mask;
   bf16* out;
-  int heads, Tq, Tk, Tk_alloc, nb, KB, KB_tail, kv_shared;   // nb key blocks: nb-1 of KB keys, the last of KB_tail (<= KB, multiple of 32)
+  const bf16* k; const bf16* v;   // [kv heads, Tk_alloc, 64]: row 0 of a head = the null key / value (read directly by the softmax warps)
+  int heads, Tq, Tk, Tk_alloc, nb, KB, KB_tail, kv_shared;   // nb blocks over the Tk - 1 real keys: nb-1 of KB keys, the last of KB_tail (<= KB, multiple of 32)
   int64_t ldo;
   float scale_log2e;
   float smax;              // > 0: caller-guaranteed bound on |q.k| -> single-pass softmax with a fixed reference maximum
@@ -92,7 +96,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
         // K(blk+1) is fetched as soon as S(blk) has retired and V(blk) while the softmax of S(blk) runs: loads are off the
         // critical path, which is  S-MMA -> softmax -> PV-MMA  per key block.
         uint32_t ph_s = 0, ph_p = 0, ph_pv = 0, ph_v = 0, ph_k = 0;
-        const int krow0 = kvh * p.Tk_alloc;
+        const int krow0 = kvh * p.Tk_alloc + 1;                  // real keys start at row 1
         mbar_expect_tx(bar_q, 16384 + kv_bytes);
         tma_load_2d(sQ, &p.tma_q, bar_q, 0, bh * p.Tq + q0);
         tma_load_2d(sK, &p.tma_k, bar_q, 0, krow0);
@@ -120,7 +124,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
       uint32_t ph_kv = 0, ph_sdone = 0, ph_p = 0, ph_pv = 0;
       for (int pass = 0; pass < 2; ++pass) {
         for (int blk = 0; blk < p.nb; ++blk) {
-          const int krow = kvh * p.Tk_alloc + blk * KB;
+          const int krow = kvh * p.Tk_alloc + 1 + blk * KB;
           mbar_expect_tx(bar_kv, pass == 0 ? kv_bytes : 2 * kv_bytes);
           tma_load_2d(sK, &p.tma_k, bar_kv, 0, krow);
           if (pass == 1) tma_load_2d(sV, &p.tma_v, bar_kv, 0, krow);
@@ -145,12 +149,32 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
     const int r = warp * 32 + lane;
     const int qi = q0 + r;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    const uint8_t* km = p.key_mask ? p.key_mask + (int64_t)b * (p.Tk - 1) : nullptr;
+    const uint8_t* km = p.key_mask ? p.key_mask + (int64_t)b * (p.Tk - 1) : nullptr;   // one byte per REAL key
+    const int Tr = p.Tk - 1;                                     // real keys
     uint32_t ph_s = 0, ph_pv = 0;
-    float row_max = -FLT_MAX, row_sum = 0.f;
+    float row_sum = 0.f;
     float mneg = 0.f;
+    // the null key: s0 = q_r . k_null (Q tile: row r at r * 128 bytes, 16-byte chunk c at position c ^ (r & 7))
+    const bf16* knull = p.k + (int64_t)kvh * p.Tk_alloc * 64;
+    float s0 = 0.f;
+    mbar_wait(bar_q, 0);                                        // Q has landed (the control warp waits on the same phase)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 qv = *reinterpret_cast<const uint4*>(sQ + r * 128 + ((c ^ (r & 7)) * 16));
+      const uint4 kv4 = __ldg(reinterpret_cast<const uint4*>(knull) + c);
+      const __nv_bfloat162* qh = reinterpret_cast<const __nv_bfloat162*>(&qv);
+      const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kv4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 a = __bfloat1622float2(qh[e]), b2 = __bfloat1622float2(kh[e]); s0 = fmaf(a.x, b2.x, s0); s0 = fmaf(a.y, b2.y, s0); }
+    }
+    float row_max = s0;                                         // the null key is always live
+    float p_null = 0.f;
     for (int pass = p.single_pass ? 1 : 0; pass < 2; ++pass) {
-      if (pass == 1) mneg = (p.single_pass ? p.smax : row_max) * p.scale_log2e;
+      if (pass == 1) {
+        mneg = (p.single_pass ? p.smax : row_max) * p.scale_log2e;
+        p_null = ex2_fast(fmaf(s0, p.scale_log2e, -mneg));
+        row_sum = p_null;
+      }
       for (int blk = 0; blk < p.nb; ++blk) {
         mbar_wait(bar_s, ph_s); ph_s ^= 1;
         tc_fence_after();
@@ -163,9 +187,9 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
           // liveness of the 32 keys of this chunk as one ballot word (lane l tests key j0 + l: ONE coalesced mask byte per lane instead of 32
           // byte loads per thread; key 0, the null key, is never masked)
           uint32_t livew = 0xffffffffu;
-          if (km || j0 + 32 > p.Tk) {
+          if (km || j0 + 32 > Tr) {
             const int jl = j0 + lane;
-            livew = __ballot_sync(0xffffffffu, jl < p.Tk && (jl == 0 || !km || km[jl - 1]));
+            livew = __ballot_sync(0xffffffffu, jl < Tr && (!km || km[jl]));
           }
           if (pass == 0) {
 #pragma unroll
@@ -176,7 +200,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
             }
           } else {
             uint32_t packed[16];
-            if (!km && j0 + 32 <= p.Tk) {
+            if (!km && j0 + 32 <= Tr) {
               // fast path (self-attention, chunk fully inside the key range): no per-key liveness tests
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
@@ -224,11 +248,24 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
     }
     tc_fence_after();
     const float inv = 1.f / row_sum;
+    const bf16* vnull = p.v + (int64_t)kvh * p.Tk_alloc * 64;
 #pragma unroll
     for (int c = 0; c < 64; c += 32) {
       float o[32];
-      tmem_ld_32x32b_x32(tO + lane_base + c, o);
-      tmem_ld_wait();
+      if (p.nb > 0) {
+        tmem_ld_32x32b_x32(tO + lane_base + c, o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;                  // no real key at all: the output is the null value
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {                          // + p_null * v_null (fp32; p_null unrounded in numerator and denominator)
+        const uint4 vv = __ldg(reinterpret_cast<const uint4*>(vnull + c + i));
+        const __nv_bfloat162* vh = reinterpret_cast<const __nv_bfloat162*>(&vv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(vh[e]); o[i + 2 * e] = fmaf(p_null, f.x, o[i + 2 * e]); o[i + 2 * e + 1] = fmaf(p_null, f.y, o[i + 2 * e + 1]); }
+      }
       if (qi < p.Tq) {
         bf16* dst = p.out + ((int64_t)b * p.Tq + qi) * p.ldo + h * 64 + c;
 #pragma unroll
@@ -251,7 +288,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
 // ---- host side -------------------------------------------------------------------------------------------------
 inline bool attention_tc_supported(const mmg_attention_args* a) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  return al(a->q) && al(a->k) && al(a->v) && al(a->out) && (a->ldo % 8 == 0) && a->Tk <= 4096;
+  return al(a->q) && al(a->k) && al(a->v) && al(a->out) && (a->ldo % 8 == 0) && a->Tk >= 2 && a->Tk <= 4096;
 }
 
 // Key blocking: nb-1 blocks of KB keys and a last block of KB_tail keys (multiple of 32).  KB = 64 keeps S (64 fp32 columns) + O (64)
