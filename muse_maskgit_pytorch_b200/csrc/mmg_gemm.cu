@@ -156,7 +156,7 @@ static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_
                          (!e.nq_heads || aligned16(e.q_out)) && (!e.nk_heads || (aligned16(e.k_out) && aligned16(e.v_out))) && e.nk_heads == e.nv_heads;
   static const int geglut_forced = [] { const char* ev = getenv("MMG_GEMM_GEGLUT"); return ev ? atoi(ev) : -1; }();
   const bool geglu_tiles = p.epi.kind == MMG_EPI_GEGLU && e.out_dtype == MMG_BF16 && p.mode == 0 && bn == 256 && (e.ldo % 8) == 0 && aligned16(e.out);
-  const int epi_mode = (in_place && red_forced != 0) ? 2 : (plain_f32 && tstore_forced != 0 && bn == 256) ? 3 : (qkv_tiles && qkvt_forced != 0) ? 4 :
+  const int epi_mode = (in_place && red_forced != 0) ? 2 : (plain_f32 && tstore_forced != 0 && (bn == 256 || bn == 128)) ? 3 : (qkv_tiles && qkvt_forced != 0) ? 4 :
                        (geglu_tiles && geglut_forced != 0) ? 5 : 0;
   const bool pair = use_pair(p, bn, epi_mode >= 4 ? 0 : epi_mode);
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; uint64_t str[1] = {(uint64_t)ldw * 2}; uint32_t box[2] = {TC_BK, (uint32_t)(pair ? bn / 2 : bn)};
@@ -183,7 +183,7 @@ static int dispatch_tc(TcGemmParams& p, int bn, const void* w, int64_t N, int64_
     rc = make_tmap_f32(&p.tma_out, e.out, 2, od, os, ob); if (rc) return rc;
   }
   if (pair) return epi_mode == 2 ? launch_tc_pair<256, 2>(p, st) : epi_mode == 3 ? launch_tc_pair<256, 3>(p, st) : launch_tc_pair<256>(p, st);
-  if (epi_mode == 3) return launch_tc_tstore<256>(p, st);
+  if (epi_mode == 3) return bn == 256 ? launch_tc_tstore<256>(p, st) : launch_tc_tstore<128>(p, st);   // 128: the sample GEMM of the fused tail at small batch
   if (epi_mode == 2) {
     switch (bn) { case 64: return launch_tc_red<64>(p, st); case 128: return launch_tc_red<128>(p, st); case 256: return launch_tc_red<256>(p, st); }
   }

@@ -587,6 +587,13 @@ def test_linear_wide_tiles_tma_epilogues():
     ok, msg = close(out[:M], a @ w.t(), 2e-4)
     assert ok, msg
     assert bool((out[M:] == 7.0).all()), "rows past M were written"
+    M, N, K = 2000, 4096, 512                     # 128-column tiles (16 x 32): the fused tail's sample GEMM at 8 images per GPU
+    a, w = rnd("sa", (M, K), bf), rnd("sw", (N, K), bf, std=K ** -0.5)
+    out = torch.full((M + 3, N), 7.0, device="cuda")
+    ops().linear(dev(a, bf), dev(w, bf), out[:M])
+    ok, msg = close(out[:M], a @ w.t(), 2e-4)
+    assert ok, msg
+    assert bool((out[M:] == 7.0).all()), "rows past M were written"
     M, N, K = 2000, 5120, 64                      # 16 x 20 tiles
     a, w, x = rnd("ra", (M, K), bf), rnd("rw", (N, K), bf, std=K ** -0.5), rnd("rx", (M, N))
     xd = dev(x)
