@@ -250,8 +250,16 @@ class VQGanVAE(nn.Module):
                 P["pin_w3"] = w3.contiguous()
         else:
             P["codebook"] = f32(q.embed)
-            P["codebook_a"] = P["codebook"].to(adt).contiguous()
-            P["code_norms"] = (P["codebook_a"].float() ** 2).sum(-1).contiguous()
+            cb = P["codebook"]
+            if adt == torch.bfloat16:
+                # the fp32 codebook as three bf16 terms along K, smallest first ([lo | mid | hi], each [codes, D]): against the token repeated
+                # three times one bf16 product accumulates x . (lo + mid + hi) = x . e in fp32 — the nearest-code argmin then sees the fp32
+                # codebook (the bf16-rounded one misplaced near-ties), at 3x the FLOPs of a lookup that is HBM-bound anyway
+                hi = cb.to(adt); r1 = cb - hi.float(); mid = r1.to(adt); lo = (r1 - mid.float()).to(adt)
+                P["codebook_a"] = torch.cat((lo, mid, hi), dim=1).contiguous()
+            else:
+                P["codebook_a"] = cb                                   # fp32: ops.linear splits both operands (mmg_split3)
+            P["code_norms"] = (cb * cb).sum(-1).contiguous()
         return P
 
     # ----- NHWC pipelines (all arithmetic in libmmg) ---------------------------------------------------------------
@@ -329,6 +337,8 @@ class VQGanVAE(nn.Module):
             ops.vq_lfq_encode(x, P["pin_w"], P["pin_b"], ids, self.quantizer.bits, w_split=P["pin_w3"] if x.dtype == torch.bfloat16 else None)
         else:
             ids.fill_(-1)                                   # all-ones keys for the packed (distance, code) atomicMin
+            if x.dtype == torch.bfloat16:
+                x = torch.cat((x, x, x), dim=1)             # against [lo | mid | hi] of the fp32 codebook
             ops.linear(x, P["codebook_a"], ids, epilogue=ops.EPI_ARGMIN, bias=P["code_norms"])
             ids &= 0xFFFFFFFF
         return ids

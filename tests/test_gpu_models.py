@@ -145,6 +145,27 @@ def test_vae_explicit_codebook_path():
     assert vae.decode_from_ids(ids).shape == (2, 3, 16, 16)
 
 
+def test_vae_explicit_codebook_bf16_argmin_sees_fp32_codebook():
+    """bf16 precision, explicit codebook at a tensor-core shape (D = 64, 1024 codes): the nearest-code search runs against the fp32 codebook
+    (three bf16 terms along K), so for the bf16 tokens the kernel is given the ids equal the fp32 L2 argmin — also where rounding the codebook to
+    bf16 would have picked another code."""
+    torch.manual_seed(5)
+    vae = M().VQGanVAE(dim=64, layers=1, codebook_size=1024, lookup_free_quantization=False, precision="bf16").cuda()
+    cb = vae.quantizer.embed.detach().float().cpu()
+    assert cb.shape == (1024, 64)
+    g = torch.Generator().manual_seed(9)
+    x = (cb[torch.randint(0, 1024, (4096,), generator=g)] + 0.3 * torch.randn((4096, 64), generator=g)).to(torch.bfloat16)
+    ids = vae._quantize_nhwc(x.cuda().contiguous()).cpu()
+    ref = O.vq_l2_argmin(x.float(), cb)
+    d = torch.cdist(x.float().double(), cb.double())
+    top2 = d.topk(2, dim=-1, largest=False).values
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-5                      # fp32 summation noise of the reference argmin itself
+    assert torch.equal(ids[clear], ref[clear])
+    rounded = O.vq_l2_argmin(x.float(), cb.to(torch.bfloat16).float())
+    print(f"explicit codebook, bf16 tokens: {int((rounded != ref).sum())} of 4096 tokens would change code with a bf16-rounded codebook; "
+          f"{int((ids != ref).sum())} differ from the fp32 argmin ({int((~clear).sum())} near-ties)")
+
+
 # ------------------------------------------------------------------------------------------------ generate
 def make_maskgit(precision, superres=False):
     m = M()
