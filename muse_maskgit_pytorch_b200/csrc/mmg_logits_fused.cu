@@ -33,9 +33,10 @@ constexpr int LF_MAX_SPLITS = 64;
 constexpr int LF_A_BYTES = LF_BM * LF_BK * 2, LF_B_BYTES = LF_BN * LF_BK * 2;
 
 // What bounds this kernel (ncu, 16 384 rows, profiles/r2_fused_tail.md): with the epilogue reduced to draining TMEM the CTA-pair main loop keeps
-// the tensor pipe 98.7 % busy (607 us), with the softmax statistics 97.5 % (624 us) — the operand feed is not the limit, and keeping A resident
-// in shared memory (half the L2 -> SM traffic) changed nothing.  The candidate emission is: it is pure issue-slot cost in the epilogue warps
-// (a predicated append per logit + the sector flushes), so the FIFO is deep enough to be drained once per 64 columns by most lanes at once.
+// the tensor pipe 98.6 % busy (621 us), with the softmax statistics 98.3 % (636 us) — the operand feed is not the limit, and keeping A resident
+// in shared memory (half the L2 -> SM traffic) changed nothing.  The candidate emission is (913 us, 67 %): it is issue cost in the epilogue warps
+// (a predicated append per logit + the sector flushes; two warps per scheduler use 52 % of the issue slots), so the FIFO is deep enough to be
+// drained once per 64 columns by most lanes at once.
 template <bool PAIR> struct LfCfg {
   static constexpr int STAGES = PAIR ? 4 : 3;
   static constexpr int STAGE_BYTES = LF_A_BYTES + (PAIR ? LF_B_BYTES / 2 : LF_B_BYTES);
