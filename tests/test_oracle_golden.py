@@ -202,3 +202,48 @@ def test_reference_written_checkpoints():
     assert torch.equal(base_ids.view(2, 4, 4), g["base_ids"]) and torch.allclose(low, g["lowres"], atol=1e-5)
     sup, sr_ids = O.generate(sub(sr, "transformer."), cfg, sub(sr, "vae."), 8, te, 8, noise, cond_images=low, sd_cond_vae=sub(sr, "cond_vae."), timesteps=4)
     assert torch.equal(sr_ids.view(2, 8, 8), g["superres_ids"]) and torch.allclose(sup, g["superres"], atol=1e-5)
+
+
+def test_split3_six_terms_carry_the_fp32_product():
+    """oracle/split3.py (the restatement of mmg_split3 the GPU tests check the kernel against): hi + mid + lo reconstructs fp32 to 2^-23 relative,
+    every term is a bf16 value, and the six cross terms of the 6K-wide product reproduce the fp64 product of the fp32 operands to ~2^-23 of
+    sum |a||w| — two orders below one bf16-operand product."""
+    from oracle import split3 as S
+    rng = np.random.default_rng(7)
+    a = (rng.standard_normal((96, 192)) * np.exp(rng.standard_normal((96, 192)) * 3)).astype(np.float32)
+    w = (rng.standard_normal((80, 192)) * 192 ** -0.5).astype(np.float32)
+    t = S.terms(a)
+    for v in t.values():
+        assert np.array_equal(S.bf16_round(v), v)                                  # each term is exactly representable in bf16
+    assert np.all(np.abs(t["hi"].astype(np.float64) + t["mid"] + t["lo"] - a) <= np.abs(a) * 2.0 ** -23)
+    assert S.split3(a, 0).shape == (96, 6 * 192) and S.split3(w, 1).shape == (80, 6 * 192)
+    exact = a.astype(np.float64) @ w.astype(np.float64).T
+    scale = np.abs(a).astype(np.float64) @ np.abs(w).astype(np.float64).T
+    err6 = np.abs(S.product(a, w) - exact) / scale
+    err1 = np.abs(S.bf16_round(a).astype(np.float64) @ S.bf16_round(w).astype(np.float64).T - exact) / scale
+    assert err6.max() < 2.0 ** -21 and err1.max() > 50 * err6.max()
+
+
+def test_gelu_polynomial_of_the_tensor_core_epilogue_is_exact_erf_gelu_to_1e6():
+    """The GEGLU epilogue's GELU (csrc/mmg_common.cuh: gelu_fast = max(x, 0) - 0.5 |x| 2^q(min(|x|, 6)), q a degree-6 polynomial for
+    log2 erfc(a / sqrt 2)) against the reference's exact-erf F.gelu (muse_maskgit_pytorch.py:76-77), evaluated here in fp32 with the
+    coefficients READ FROM THE KERNEL SOURCE: max abs error < 1e-6 over [-12, 12], relative error < 2e-4 wherever |gelu| > 1e-3."""
+    import re
+    from scipy.special import erf
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "muse_maskgit_pytorch_b200", "csrc", "mmg_common.cuh")).read()
+    body = src[src.index("float gelu_fast(float x)"):]
+    body = body[:body.index("return fmaf(-0.5f * a, e, fmaxf(x, 0.0f));")]
+    c = [np.float32(v) for v in re.findall(r"(-?\d+\.\d+(?:e-?\d+)?)f", body)]
+    assert len(c) == 7 and c[0] == np.float32(6.0), c                                # clamp, then c6, c5, c4, c3, c2, c1 in Horner order
+    x = np.linspace(-12, 12, 480001).astype(np.float32)
+    a = np.abs(x); aq = np.minimum(a, c[0])
+    q = (c[1] * aq + c[2]).astype(np.float32)
+    for ci in c[3:]:
+        q = (q * aq + ci).astype(np.float32)
+    e = np.exp2((q * aq).astype(np.float64)).astype(np.float32)
+    got = (np.maximum(x, np.float32(0)) - np.float32(0.5) * a * e).astype(np.float32)
+    ref = 0.5 * x.astype(np.float64) * (1.0 + erf(x.astype(np.float64) / np.sqrt(2.0)))
+    err = np.abs(got - ref)
+    assert err.max() < 1e-6, err.max()
+    big = np.abs(ref) > 1e-3
+    assert (err[big] / np.abs(ref[big])).max() < 2e-4
