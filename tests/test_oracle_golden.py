@@ -247,3 +247,35 @@ def test_gelu_polynomial_of_the_tensor_core_epilogue_is_exact_erf_gelu_to_1e6():
     assert err.max() < 1e-6, err.max()
     big = np.abs(ref) > 1e-3
     assert (err[big] / np.abs(ref[big])).max() < 2e-4
+
+
+def test_fused_tail_selection_equals_topk_gumbel_argmax():
+    """oracle/fused_tail.py: the candidate-list procedure of the fused sampling tail (threshold superset, perturbed argmax, exact-rank test,
+    exclusion + repeat) picks the reference's token on rows with ties, flat rows (many repeats) and peaked rows, for thresholds anywhere between
+    'barely k candidates' and 'the whole row'."""
+    from oracle import fused_tail as FT
+    rng = np.random.default_rng(11)
+    V, k = 2048, 205
+    repeats = 0
+    for case in range(60):
+        kind = case % 4
+        if kind == 0:
+            logits = rng.standard_normal(V).astype(np.float32)
+        elif kind == 1:
+            logits = np.round(rng.standard_normal(V) * 2).astype(np.float32) / 2          # heavy ties, also across the k-th value
+        elif kind == 2:
+            logits = (rng.standard_normal(V) * 0.01).astype(np.float32)                     # flat: the winner often falls outside the top-k
+        else:
+            logits = (rng.standard_normal(V) * 6).astype(np.float32)                        # peaked
+        u = rng.random(V).astype(np.float32)
+        g = (-np.log(np.maximum(-np.log(np.maximum(u, 1e-20)), 1e-20))).astype(np.float32)
+        T = [1.0, 0.3, 2.5][case % 3]
+        want = FT.reference_choice(logits, g, k, T)
+        srt = np.sort(logits)[::-1]
+        for n_cand in (k, k + 1, k + 40, 2 * k, V):
+            thr = srt[n_cand - 1]
+            got, passes = FT.fused_choice(logits, g, k, T, thr, max_excl=V)
+            assert got == want, (case, n_cand, got, want)
+            repeats += passes - 1
+        assert FT.fused_choice(logits, g, k, T, np.float32(np.inf))[0] is None              # fewer than k candidates: materialised path
+    assert repeats > 0                                                                       # the exclusion path was exercised
