@@ -187,7 +187,7 @@ def attention(q, k, v, out, B, heads, Tk, key_mask=None, kv_shared=False, scale=
     a = L.AttentionArgs()
     _chk(q); _chk(k); _chk(v)
     Tq, Tk_alloc, dtype = q.shape[1], k.shape[1], L.dt(q)
-    if q.dtype == torch.float32 and _FP32_TC[0] and Tk <= 4096 and out.dtype == torch.float32 and out.stride(0) % 4 == 0:
+    if q.dtype == torch.float32 and _FP32_TC[0] and 2 <= Tk <= 4096 and out.dtype == torch.float32 and out.stride(0) % 8 == 0:
         # fp32 parity on the tensor cores: three bf16 terms per operand, six cross terms per product (mmg_attention_split.cuh)
         q, k, v = split3(q.view(-1, 64), 0), split3(k.view(-1, 64), 1), split3(v.view(-1, 64), 1)
         dtype = L.BF16; a.split3 = 1
