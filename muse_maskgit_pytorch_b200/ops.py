@@ -82,6 +82,8 @@ def linear(a, w, out, epilogue=EPI_STORE, bias=None, act=0, resid=None, M=None, 
     args.N = w.shape[0] if N is None else N
     args.K = a.shape[1]; args.lda = a.stride(0); args.ldw = w.stride(0)
     args.dtype = L.dt(a); args.epilogue = epilogue
+    if epilogue in (EPI_GEGLU, EPI_GLU) and out is not None:
+        assert out.shape[-1] * 2 >= args.N and out.stride(0) * 2 >= args.N, "GEGLU / GLU write N / 2 columns per row: `out` is too narrow"
     if epi is None:
         epi = _epi(out, out.stride(0), bias, act, resid, resid.stride(0) if resid is not None else 0, row_stats, ln_width)
         if ln_out is not None:      # fused LayerNorm of the output rows (bf16) for the next matrix product
